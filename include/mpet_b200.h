@@ -1,0 +1,144 @@
+/*
+ * mpet_b200.h -- C-ABI of libmpet_b200.so: the B200-native (sm_100a) replacement for the
+ * per-timestep assemble + Krylov-solve path of waterscapes' `mpet` solver.
+ *
+ * The reference has no FFI of its own; its boundary for this path is the DOLFIN/PETSc Python API
+ * used by src/mpet/mpet/mpetsolver.py.  Each entry point below names the reference call it replaces
+ * (paths relative to the reference checkout, `mpetsolver.py` = src/mpet/mpet/mpetsolver.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; mpet_last_error(ctx) gives the message.
+ *     No C++ exception crosses this boundary.
+ *   - "dev" pointers are DEVICE pointers owned by the caller (torch tensors: tensor.data_ptr());
+ *     "host" pointers are ordinary host memory.  The library never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *     Calls are asynchronous w.r.t. the host unless stated otherwise.
+ *   - one ctx per GPU and per host thread; not thread-safe.
+ *   - all floating-point data is fp64; dof / column indices are int32, CSR row pointers int64.
+ *
+ * Dof numbering (UFC numbering of MixedElement([P2^3] + [P1]*A), mpetsolver.py:100-132):
+ *   displacement component k, scalar P2 node n  ->  k*N2 + n      (n < Nv: vertex, else Nv + edge)
+ *   pressure i, vertex v                        ->  3*N2 + i*Nv + v
+ *   edges are numbered lexicographically by (lo vertex, hi vertex).
+ */
+#ifndef MPET_B200_H
+#define MPET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpet_ctx mpet_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int mpet_create(int device, mpet_ctx** out);
+void mpet_destroy(mpet_ctx* ctx);
+const char* mpet_last_error(mpet_ctx* ctx);
+int mpet_abi_version(void);
+
+/* ---- function space + sparsity graph (built once, on device) ----------------------------------
+ * Replaces FunctionSpace(mesh, MixedElement(...)) (mpetsolver.py:126-130: dof map) and DOLFIN's
+ * SparsityPatternBuilder + PETScMatrix::init inside assemble() (mpetsolver.py:335,412,496).
+ * coords_dev f64[nv*3], cells_dev i32[nc*4] (each cell's vertices ascending).  Synchronous. */
+int mpet_set_mesh(mpet_ctx* ctx, const double* coords_dev, const int32_t* cells_dev,
+                  int64_t nv, int64_t nc, int n_networks, void* stream);
+
+/* sizes[0..9] = Nv, Ne, N2, Nc, N, nnz, nnz22, nnz21, nnz11, n_networks */
+int mpet_get_sizes(mpet_ctx* ctx, int64_t* sizes_host);
+/* edge_vertices i32[Ne*2]; cell_dofs i32[Nc*(30+4A)] in UFC local order (device outputs) */
+int mpet_get_edges(mpet_ctx* ctx, int32_t* edge_vertices_dev, void* stream);
+int mpet_get_cell_dofs(mpet_ctx* ctx, int32_t* cell_dofs_dev, void* stream);
+/* CSR pattern of the block system: rowptr i64[N+1], cols i32[nnz] (ascending per row) */
+int mpet_get_pattern(mpet_ctx* ctx, int64_t* rowptr_dev, int32_t* cols_dev, void* stream);
+
+/* ---- coefficients ------------------------------------------------------------------------------
+ * Replaces the Constants captured by create_variational_forms (mpetsolver.py:183-189) and
+ * solver.dt.assign / params["dt"], params["theta"] (mpetsolver.py:137,179,329-330).
+ * alpha, K, c: host f64[A]; S: host f64[A*A] row-major. */
+int mpet_set_params(mpet_ctx* ctx, double E, double nu, const double* alpha_host,
+                    const double* K_host, const double* S_host, const double* c_host,
+                    double dt, double theta);
+
+/* ---- matrix assembly ---------------------------------------------------------------------------
+ * mpet_assemble_lhs  : A = assemble(a)                       (mpetsolver.py:335,412,496; form :196-201,260)
+ * mpet_add_entries   : A.axpy(1.0, assemble(a_robin[i]))     (mpetsolver.py:336-338; form :252-253)
+ *                      rows/cols i32[n], vals f64[n] on device, (row,col) pairs unique
+ * mpet_assemble_prec : P = assemble(prec)                    (mpetsolver.py:264-277,502; well-formed
+ *                      analogue mpettotalpressuresolver.py:276-283): scalar P2 block mu*(grad,grad)
+ *                      shared by the 3 displacement components + one P1 block per network.
+ * mpet_get_values    : copy values to caller memory (device), laid out on mpet_get_pattern's CSR.
+ *                      which = 0: A as assembled (no BCs)
+ *                              1: A after bc.apply(A)            (rows zeroed, unit diagonal)
+ *                              2: A after apply_symmetric(bc, A) (bc_symmetric.py:11-22)
+ *                              3: block-diagonal P expanded on the full pattern, symmetric BCs applied
+ */
+int mpet_assemble_lhs(mpet_ctx* ctx, void* stream);
+int mpet_add_entries(mpet_ctx* ctx, const int32_t* rows_dev, const int32_t* cols_dev,
+                     const double* vals_dev, int64_t n, void* stream);
+int mpet_assemble_prec(mpet_ctx* ctx, void* stream);
+int mpet_get_values(mpet_ctx* ctx, int which, double* vals_dev, void* stream);
+
+/* ---- Dirichlet conditions ----------------------------------------------------------------------
+ * Replaces create_dirichlet_bcs (mpetsolver.py:63-84) / DirichletBC.get_boundary_values:
+ * the dof set is fixed; values change every step.  dofs i32[n] (device), unique. */
+int mpet_set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs_dev, int64_t n, void* stream);
+int mpet_set_dirichlet_values(mpet_ctx* ctx, const double* vals_dev, void* stream);
+
+/* ---- right-hand side ---------------------------------------------------------------------------
+ * mpet_rhs_prev : b  = assemble(L)   previous-state load   (mpetsolver.py:356,433,528; L = rhs(F) :261)
+ * mpet_mass_apply: y += scale * M x  with the consistent mass of the chosen scalar space
+ *                  space = 2: P2 (x, y are N2 long)   -> int f_k phi_a   (L0, mpetsolver.py:233)
+ *                  space = 1: P1 (x, y are Nv long)   -> int g_i psi_m   (L1, mpetsolver.py:249)
+ * mpet_lumped   : w[n] = int phi_n dx for the scalar space (constant-coefficient loads)
+ * mpet_apply_dirichlet_rhs : bc.apply(b): b[dof] = value   (mpetsolver.py:375-376,452-453)
+ */
+int mpet_rhs_prev(mpet_ctx* ctx, const double* up_prev_dev, double* b_dev, void* stream);
+int mpet_mass_apply(mpet_ctx* ctx, int space, double scale, const double* x_dev, double* y_dev,
+                    void* stream);
+int mpet_lumped(mpet_ctx* ctx, int space, double* w_dev, void* stream);
+int mpet_apply_dirichlet_rhs(mpet_ctx* ctx, double* b_dev, void* stream);
+
+/* ---- sparse kernels exposed for measurement and tests ------------------------------------------
+ * y = A x on the assembled block matrix (no BC masking); what PETSc MatMult does inside KSP. */
+int mpet_spmv(mpet_ctx* ctx, const double* x_dev, double* y_dev, void* stream);
+/* generic CSR SpMV on caller-owned arrays (tests / facet operators) */
+int mpet_csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr_dev, const int32_t* cols_dev,
+                  const double* vals_dev, const double* x_dev, double* y_dev, double beta,
+                  void* stream);
+
+/* ---- Krylov solve ------------------------------------------------------------------------------
+ * Replaces PETScKrylovSolver("minres","hypre_amg") + set_operators(A, P) + solve(x, b)
+ * (mpetsolver.py:507,553,556; mpettotalpressuresolver.py:448,492-493) and, for parity with the
+ * default path, LUSolver(A,"mumps").solve (mpetsolver.py:347,379,422,456) when run to tight rtol.
+ * method: 0 = MINRES (symmetric S), 1 = restarted GMRES (any S).
+ * pc    : 0 = none, 1 = Jacobi, 2 = block-diagonal AMG V-cycle (needs mpet_assemble_prec first).
+ * mpet_pc_setup builds the AMG hierarchies from the current P (once per dt).
+ * mpet_solve: x_dev holds the initial guess on entry (Dirichlet entries are overwritten with the
+ * boundary values), the solution on exit.  Convergence: ||r||_{M^-1} <= max(rtol*||r0||_{M^-1}, atol)
+ * (PETSc's default preconditioned-norm test).  Synchronous.  info_host[0] = iterations,
+ * [1] = converged flag, [2] = final relative residual, [3] = initial residual norm. */
+int mpet_krylov_setup(mpet_ctx* ctx, int method, int pc, double rtol, double atol, int maxit,
+                      int restart);
+int mpet_pc_setup(mpet_ctx* ctx, void* stream);
+int mpet_solve(mpet_ctx* ctx, const double* b_dev, double* x_dev, double* info_host, void* stream);
+/* apply the preconditioner once: z = M^-1 r (tests) */
+int mpet_pc_apply(mpet_ctx* ctx, const double* r_dev, double* z_dev, void* stream);
+
+/* ---- multi-GPU (one process per GPU; rows owned by rank, ghost columns exchanged over NVLink) ---
+ * nccl_uid_host: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host plumbing. */
+int mpet_attach_comm(mpet_ctx* ctx, const void* nccl_uid_host, int rank, int nranks);
+/* owned/ghost layout of this rank's dofs, see DESIGN.md "Multi-GPU" */
+int mpet_set_partition(mpet_ctx* ctx, const int32_t* owner_of_local_dof_dev, int64_t n_owned,
+                       void* stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------------
+ * number of kernels this library launched since the last reset (bench.py's "gpu_launches") */
+int64_t mpet_launch_count(mpet_ctx* ctx, int reset);
+int64_t mpet_device_bytes(mpet_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPET_B200_H */

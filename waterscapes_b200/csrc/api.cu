@@ -1,0 +1,304 @@
+// extern "C" entry points of libmpet_b200.so (see include/mpet_b200.h for the contract).
+#include "ctx.h"
+#include <cstring>
+
+// rhs.cu
+void rhs_prev(mpet_ctx* ctx, const double* up, double* b, cudaStream_t st);
+void export_values(mpet_ctx* ctx, int which, double* out, cudaStream_t st);
+void set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, cudaStream_t st);
+void scatter_bc_values(mpet_ctx* ctx, double* out, cudaStream_t st);
+void add_entries(mpet_ctx* ctx, const int32_t* r, const int32_t* c, const double* v, int64_t n, cudaStream_t st);
+// krylov.cu / amg.cu
+void krylov_free(mpet_ctx* ctx);
+void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st);
+void pc_setup(mpet_ctx* ctx, cudaStream_t st);
+void pc_apply(mpet_ctx* ctx, const double* r, double* z, cudaStream_t st);
+void amg_free(mpet_ctx* ctx);
+// dist.cu
+void dist_attach(mpet_ctx* ctx, const void* uid, int rank, int nranks);
+void dist_free(mpet_ctx* ctx);
+
+namespace {
+__global__ void k_cell_dofs(const int32_t* __restrict__ cell_nodes, int64_t nc, int64_t n2, int64_t nv,
+                            int A, int32_t* __restrict__ out) {
+    int nloc = 30 + 4 * A;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nc * nloc) return;
+    int64_t c = i / nloc;
+    int l = (int)(i - c * nloc);
+    if (l < 30) {
+        int k = l / 10, a = l - 10 * k;
+        out[i] = (int32_t)(k * n2 + cell_nodes[c * 10 + a]);
+    } else {
+        int q = l - 30;
+        int n = q / 4, m = q - 4 * n;
+        out[i] = (int32_t)(3 * n2 + n * nv + cell_nodes[c * 10 + m]);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int mpet_abi_version(void) { return 1; }
+
+int mpet_create(int device, mpet_ctx** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    mpet_ctx* ctx = new (std::nothrow) mpet_ctx();
+    if (!ctx) return -1;
+    ctx->device = device;
+    *out = ctx;
+    MPET_TRY(ctx)
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    MPET_REQUIRE(prop.major >= 10, "libmpet_b200 is built for sm_100a (Blackwell B200) only");
+    init_reference_tables();
+    MPET_CATCH(ctx)
+}
+
+void mpet_destroy(mpet_ctx* ctx) {
+    if (!ctx) return;
+    try {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        krylov_free(ctx);
+        amg_free(ctx);
+        dist_free(ctx);
+        for (void* p : ctx->allocs) cudaFree(p);
+    } catch (...) {
+    }
+    delete ctx;
+}
+
+const char* mpet_last_error(mpet_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mpet_set_mesh(mpet_ctx* ctx, const double* coords_dev, const int32_t* cells_dev, int64_t nv,
+                  int64_t nc, int n_networks, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->Nc == 0, "mesh already set on this context");
+    MPET_REQUIRE(nv > 0 && nc > 0, "empty mesh");
+    MPET_REQUIRE(n_networks >= 0 && n_networks <= MPET_MAX_NETWORKS, "unsupported number of networks");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    ctx->Nv = nv;
+    ctx->Nc = nc;
+    ctx->A = n_networks;
+    ctx->coords = dev_alloc<double>(ctx, nv * 3);
+    ctx->cells = dev_alloc<int32_t>(ctx, nc * 4);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->coords, coords_dev, sizeof(double) * nv * 3, cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->cells, cells_dev, sizeof(int32_t) * nc * 4, cudaMemcpyDeviceToDevice, st));
+    build_space(ctx, st);
+    compute_geometry(ctx, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    MPET_CATCH(ctx)
+}
+
+int mpet_get_sizes(mpet_ctx* ctx, int64_t* s) {
+    MPET_TRY(ctx)
+    s[0] = ctx->Nv; s[1] = ctx->Ne; s[2] = ctx->N2; s[3] = ctx->Nc; s[4] = ctx->N; s[5] = ctx->nnz;
+    s[6] = ctx->g22.nnz; s[7] = ctx->g21.nnz; s[8] = ctx->g11.nnz; s[9] = ctx->A;
+    MPET_CATCH(ctx)
+}
+
+int mpet_get_edges(mpet_ctx* ctx, int32_t* out, void* stream) {
+    MPET_TRY(ctx)
+    CUDA_CHECK(cudaMemcpyAsync(out, ctx->edge_v, sizeof(int32_t) * 2 * ctx->Ne, cudaMemcpyDeviceToDevice,
+                               as_stream(stream)));
+    MPET_CATCH(ctx)
+}
+
+int mpet_get_cell_dofs(mpet_ctx* ctx, int32_t* out, void* stream) {
+    MPET_TRY(ctx)
+    int64_t n = ctx->Nc * ctx->nloc;
+    k_cell_dofs<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(ctx->cell_nodes, ctx->Nc, ctx->N2, ctx->Nv,
+                                                                 ctx->A, out);
+    LAUNCH_CHECK(ctx);
+    MPET_CATCH(ctx)
+}
+
+int mpet_get_pattern(mpet_ctx* ctx, int64_t* rowptr, int32_t* cols, void* stream) {
+    MPET_TRY(ctx)
+    cudaStream_t st = as_stream(stream);
+    CUDA_CHECK(cudaMemcpyAsync(rowptr, ctx->rowptr, sizeof(int64_t) * (ctx->N + 1), cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(cols, ctx->cols, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToDevice, st));
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_params(mpet_ctx* ctx, double E, double nu, const double* alpha, const double* K,
+                    const double* S, const double* c, double dt, double theta) {
+    MPET_TRY(ctx)
+    const int A = ctx->A;
+    MPET_REQUIRE(ctx->Nc > 0, "mpet_set_mesh must be called first");
+    ctx->E = E;
+    ctx->nu = nu;
+    ctx->mu = E / (2.0 * (1.0 + nu));                           // mpetproblem.py:13-16
+    ctx->lmbda = nu * E / ((1.0 - 2.0 * nu) * (1.0 + nu));
+    for (int i = 0; i < A; ++i) {
+        ctx->alpha[i] = alpha[i];
+        ctx->K[i] = K[i];
+        ctx->c[i] = c[i];
+        for (int j = 0; j < A; ++j) ctx->S[i * A + j] = S[i * A + j];
+    }
+    ctx->dt = dt;
+    ctx->theta = theta;
+    ctx->params_set = true;
+    MPET_CATCH(ctx)
+}
+
+int mpet_assemble_lhs(mpet_ctx* ctx, void* stream) {
+    MPET_TRY(ctx)
+    assemble_lhs(ctx, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_add_entries(mpet_ctx* ctx, const int32_t* rows, const int32_t* cols, const double* vals,
+                     int64_t n, void* stream) {
+    MPET_TRY(ctx)
+    add_entries(ctx, rows, cols, vals, n, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_assemble_prec(mpet_ctx* ctx, void* stream) {
+    MPET_TRY(ctx)
+    assemble_prec(ctx, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_get_values(mpet_ctx* ctx, int which, double* vals, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(which >= 0 && which <= 3, "which must be 0..3");
+    export_values(ctx, which, vals, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->N > 0, "mpet_set_mesh must be called first");
+    set_dirichlet_dofs(ctx, dofs, n, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_dirichlet_values(mpet_ctx* ctx, const double* vals, void* stream) {
+    MPET_TRY(ctx)
+    if (ctx->n_bc > 0)
+        CUDA_CHECK(cudaMemcpyAsync(ctx->bc_vals, vals, sizeof(double) * ctx->n_bc, cudaMemcpyDeviceToDevice,
+                                   as_stream(stream)));
+    MPET_CATCH(ctx)
+}
+
+int mpet_rhs_prev(mpet_ctx* ctx, const double* up_prev, double* b, void* stream) {
+    MPET_TRY(ctx)
+    rhs_prev(ctx, up_prev, b, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_mass_apply(mpet_ctx* ctx, int space, double scale, const double* x, double* y, void* stream) {
+    MPET_TRY(ctx)
+    cudaStream_t st = as_stream(stream);
+    DevCsr M;
+    if (space == 2) {
+        ensure_m22(ctx, st);
+        M.nrows = M.ncols = ctx->N2; M.nnz = ctx->g22.nnz;
+        M.rowptr = ctx->g22.rowptr; M.col = ctx->g22.col; M.val = ctx->m22;
+    } else if (space == 1) {
+        MPET_REQUIRE(ctx->lhs_ready || ctx->prec_ready, "assemble first (P1 mass is a by-product)");
+        M.nrows = M.ncols = ctx->Nv; M.nnz = ctx->g11.nnz;
+        M.rowptr = ctx->g11.rowptr; M.col = ctx->g11.col; M.val = ctx->m11;
+    } else {
+        MPET_REQUIRE(false, "space must be 1 (P1) or 2 (P2)");
+    }
+    csr32_spmm(ctx, M, x, M.ncols, y, M.nrows, 1, scale, 1.0, st);
+    MPET_CATCH(ctx)
+}
+
+int mpet_lumped(mpet_ctx* ctx, int space, double* w, void* stream) {
+    MPET_TRY(ctx)
+    cudaStream_t st = as_stream(stream);
+    int64_t n = (space == 2) ? ctx->N2 : ctx->Nv;
+    std::vector<double> ones((size_t)n, 1.0);
+    double* d1 = nullptr;
+    CUDA_CHECK(cudaMalloc(&d1, sizeof(double) * n));
+    CUDA_CHECK(cudaMemcpyAsync(d1, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemsetAsync(w, 0, sizeof(double) * n, st));
+    int rc = mpet_mass_apply(ctx, space, 1.0, d1, w, stream);
+    cudaStreamSynchronize(st);
+    cudaFree(d1);
+    if (rc) return rc;
+    MPET_CATCH(ctx)
+}
+
+int mpet_apply_dirichlet_rhs(mpet_ctx* ctx, double* b, void* stream) {
+    MPET_TRY(ctx)
+    scatter_bc_values(ctx, b, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_spmv(mpet_ctx* ctx, const double* x, double* y, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run first");
+    csr_spmv(ctx, ctx->N, ctx->rowptr, ctx->cols, ctx->vals, x, y, 0.0, nullptr, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
+                  const double* vals, const double* x, double* y, double beta, void* stream) {
+    MPET_TRY(ctx)
+    csr_spmv(ctx, nrows, rowptr, cols, vals, x, y, beta, nullptr, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_krylov_setup(mpet_ctx* ctx, int method, int pc, double rtol, double atol, int maxit, int restart) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(method == 0 || method == 1, "method: 0 = MINRES, 1 = GMRES");
+    MPET_REQUIRE(pc >= 0 && pc <= 2, "pc: 0 = none, 1 = Jacobi, 2 = block AMG");
+    ctx->method = method;
+    ctx->pc = pc;
+    ctx->rtol = rtol;
+    ctx->atol = atol;
+    ctx->maxit = maxit;
+    ctx->restart = restart > 0 ? restart : 30;
+    MPET_CATCH(ctx)
+}
+
+int mpet_pc_setup(mpet_ctx* ctx, void* stream) {
+    MPET_TRY(ctx)
+    pc_setup(ctx, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_solve(mpet_ctx* ctx, const double* b, double* x, double* info, void* stream) {
+    MPET_TRY(ctx)
+    krylov_solve(ctx, b, x, info, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_pc_apply(mpet_ctx* ctx, const double* r, double* z, void* stream) {
+    MPET_TRY(ctx)
+    pc_apply(ctx, r, z, as_stream(stream));
+    MPET_CATCH(ctx)
+}
+
+int mpet_attach_comm(mpet_ctx* ctx, const void* uid, int rank, int nranks) {
+    MPET_TRY(ctx)
+    dist_attach(ctx, uid, rank, nranks);
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_partition(mpet_ctx* ctx, const int32_t* owner, int64_t n_owned, void* stream) {
+    MPET_TRY(ctx)
+    (void)owner; (void)n_owned; (void)stream;
+    MPET_REQUIRE(false, "mpet_set_partition: not implemented yet");
+    MPET_CATCH(ctx)
+}
+
+int64_t mpet_launch_count(mpet_ctx* ctx, int reset) {
+    int64_t n = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return n;
+}
+
+int64_t mpet_device_bytes(mpet_ctx* ctx) { return ctx->bytes; }
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// Internal context of libmpet_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <exception>
+#include <stdexcept>
+#include <cstdio>
+
+#include "../../include/mpet_b200.h"
+
+#define MPET_MAX_NETWORKS 8
+
+struct MpetError : public std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CUDA_CHECK(call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            char buf__[512];                                                               \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,    \
+                     cudaGetErrorString(e__));                                             \
+            throw MpetError(buf__);                                                        \
+        }                                                                                  \
+    } while (0)
+
+#define MPET_REQUIRE(cond, msg)                                                            \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            char buf__[512];                                                               \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s", __FILE__, __LINE__, msg);           \
+            throw MpetError(buf__);                                                        \
+        }                                                                                  \
+    } while (0)
+
+// A scalar CSR graph between two node sets (P2 nodes = "2", P1 vertices = "1").
+struct NodeGraph {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int32_t* rowptr = nullptr;   // [nrows+1]
+    int32_t* col = nullptr;      // [nnz] ascending per row
+    int32_t* gptr = nullptr;     // [nnz+1] offsets into glist (contributions per entry)
+    uint32_t* glist = nullptr;   // [ncontrib] cell * npairs + local pair id, ascending cell per entry
+    int64_t ncontrib = 0;
+};
+
+// Generic device CSR matrix (AMG levels, facet operators).
+struct DevCsr {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int32_t* rowptr = nullptr;
+    int32_t* col = nullptr;
+    double* val = nullptr;
+};
+
+struct AmgLevel {
+    DevCsr A;            // operator on this level (Dirichlet rows = identity)
+    DevCsr P;            // prolongation from the next coarser level (nrows = this level)
+    DevCsr R;            // restriction = P^T
+    double* dinv = nullptr;   // inverse diagonal
+    double* x = nullptr;      // [nrhs * n] work vectors
+    double* b = nullptr;
+    double* r = nullptr;
+    double* t = nullptr;
+    double lambda_max = 0.0;  // estimate of rho(D^-1 A)
+};
+
+struct AmgHierarchy {
+    std::vector<AmgLevel> levels;
+    int nrhs = 1;
+    double* coarse_inv = nullptr;  // dense inverse on the coarsest level
+    int64_t coarse_n = 0;
+};
+
+struct mpet_ctx {
+    int device = 0;
+    std::string err;
+    int64_t launches = 0;
+    int64_t bytes = 0;
+    std::vector<void*> allocs;
+    int sm_count = 148;
+
+    // mesh / space
+    int64_t Nv = 0, Ne = 0, N2 = 0, Nc = 0, N = 0, nnz = 0;
+    int A = 0;                   // networks
+    int nloc = 0;
+    double* coords = nullptr;    // [Nv*3] (library copy)
+    int32_t* cells = nullptr;    // [Nc*4]
+    int32_t* edge_v = nullptr;   // [Ne*2]
+    int32_t* cell_nodes = nullptr;  // [Nc*10] scalar P2 nodes of each cell
+    double* geom = nullptr;      // [Nc*10]: Jinv (row-major 3x3: Jinv[k][m] = dX_k/dx_m), |detJ|
+    NodeGraph g22, g21, g12, g11;
+    int32_t* t21to12 = nullptr;  // [nnz21] position of the transposed entry in g12
+    int64_t* rowptr = nullptr;   // [N+1] block-system CSR
+    int32_t* cols = nullptr;     // [nnz]
+    double* vals = nullptr;      // [nnz] A as assembled (never modified by BCs)
+    // scalar operators kept beside A
+    double* m11 = nullptr;       // [nnz11] P1 mass
+    double* l11 = nullptr;       // [nnz11] P1 stiffness
+    double* m22 = nullptr;       // [nnz22] P2 mass (lazy)
+    double* k22 = nullptr;       // [nnz22] P2 stiffness (grad,grad) (prec, lazy)
+    double* pp11 = nullptr;      // [A*nnz11] preconditioner pressure blocks
+
+    // coefficients
+    double E = 0, nu = 0, mu = 0, lmbda = 0, dt = 0, theta = 1;
+    double alpha[MPET_MAX_NETWORKS], K[MPET_MAX_NETWORKS], c[MPET_MAX_NETWORKS];
+    double S[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
+    bool params_set = false, lhs_ready = false, prec_ready = false;
+
+    // Dirichlet
+    int64_t n_bc = 0;
+    int32_t* bc_dofs = nullptr;
+    double* bc_vals = nullptr;
+    uint8_t* bc_mask = nullptr;  // [N] 1 on Dirichlet rows
+
+    // Krylov
+    int method = 0, pc = 2, maxit = 10000, restart = 30;
+    double rtol = 1e-5, atol = 1e-50;
+    struct KrylovWork* kw = nullptr;
+    AmgHierarchy* amg_u = nullptr;              // scalar P2 block, 3 right-hand sides
+    AmgHierarchy* amg_p[MPET_MAX_NETWORKS] = {};  // one per network
+    double* jac_dinv = nullptr;                 // Jacobi preconditioner (pc = 1)
+};
+
+// ---- helpers --------------------------------------------------------------------------------
+template <typename T>
+T* dev_alloc(mpet_ctx* ctx, int64_t n) {
+    if (n <= 0) n = 1;
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, (size_t)n * sizeof(T)));
+    ctx->allocs.push_back(p);
+    ctx->bytes += n * (int64_t)sizeof(T);
+    return (T*)p;
+}
+void dev_free(mpet_ctx* ctx, void* p);
+
+#define MPET_TRY(ctx) try {
+#define MPET_CATCH(ctx)                                                    \
+    }                                                                      \
+    catch (const std::exception& e__) {                                    \
+        if (ctx) (ctx)->err = e__.what();                                  \
+        return -1;                                                         \
+    }                                                                      \
+    return 0;
+
+inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+inline int grid_for(int64_t work, int block) {
+    int64_t g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > 2147483647LL) g = 2147483647LL;
+    return (int)g;
+}
+
+#define LAUNCH_CHECK(ctx)             \
+    do {                              \
+        (ctx)->launches++;            \
+        CUDA_CHECK(cudaGetLastError()); \
+    } while (0)
+
+// graph.cu
+void build_space(mpet_ctx* ctx, cudaStream_t st);
+// assemble.cu
+void init_reference_tables();
+void compute_geometry(mpet_ctx* ctx, cudaStream_t st);
+void assemble_lhs(mpet_ctx* ctx, cudaStream_t st);
+void assemble_prec(mpet_ctx* ctx, cudaStream_t st);
+void ensure_m22(mpet_ctx* ctx, cudaStream_t st);
+// spmv.cu
+void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
+              const double* vals, const double* x, double* y, double beta, const uint8_t* rowmask,
+              cudaStream_t st);
+void csr32_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, double* y, int64_t ldy,
+                int nrhs, double alpha, double beta, cudaStream_t st);
