@@ -1,0 +1,718 @@
+// Block-diagonal AMG preconditioner: one V-cycle per field block, applied entirely on device.
+//
+// Replaces PC "hypre_amg" (one BoomerAMG V-cycle on the assembled block-diagonal matrix P,
+// mpetsolver.py:502-507, mpettotalpressuresolver.py:443-448).  P's structure is exploited instead of
+// treating it as one big matrix:
+//   * displacement: the three components share ONE scalar P2 operator mu*(grad,grad)
+//     (mpetsolver.py:268-269) -> one hierarchy applied to 3 right-hand sides at once (the matrix is
+//     streamed once per SpMM).  Level 0 -> 1 is p-coarsening P2 -> P1 (P1 is a subspace of P2, so the
+//     Galerkin operator is the P1 stiffness matrix, assembled directly by assemble.cu); below that,
+//     smoothed aggregation.
+//   * each network pressure: its own P1 operator (c_i + dt theta sum S_ij) M + dt theta K_i L
+//     (mpetsolver.py:270-271), smoothed aggregation below.
+// Smoother: Chebyshev polynomial in D^-1 A (symmetric, no triangular solves: GPU-friendly stand-in
+// for BoomerAMG's hybrid Gauss-Seidel), fused with the SpMM that produces its residual.  With equal
+// pre/post smoothing and a zero initial guess the V-cycle is a fixed SPD operator, as MINRES needs.
+// The aggregation set-up (strength graph, aggregates, smoothed prolongator, Galerkin product) runs
+// once per (mesh, dt) on the host in this translation unit on the small P1-sized matrices and is
+// uploaded; everything per-iteration is device code.
+#include "ctx.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace {
+
+// =============================================================================== device kernels
+__device__ __forceinline__ double ldg_stream(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int32_t ldg_stream(const int32_t* p) {
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+enum { EPI_RESID = 0, EPI_CHEB = 1 };
+
+// Fused SpMM + epilogue over NRHS vectors (leading dimension ld for every vector array):
+//   EPI_RESID: out = b - A x
+//   EPI_CHEB : r = b - A x ; d = c1*d + c2*dinv*r ; xout = x + d
+template <int LANES, int NRHS, int EPI>
+__global__ void __launch_bounds__(256)
+k_spmm_epi(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
+           const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ b,
+           double* __restrict__ out, double* __restrict__ d, const double* __restrict__ dinv, double c1,
+           double c2, int64_t ldx, int64_t ldb, int64_t ldo, int64_t ldd, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int lane = threadIdx.x & (LANES - 1);
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    if (row >= nrows) return;
+    const int32_t s = rowptr[row], e = rowptr[row + 1];
+    double sum[NRHS];
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) sum[k] = 0.0;
+    for (int32_t i = s + lane; i < e; i += LANES) {
+        double v = ldg_stream(vals + i);
+        int32_t c = ldg_stream(cols + i);
+#pragma unroll
+        for (int k = 0; k < NRHS; ++k) sum[k] += v * __ldg(x + k * ldx + c);
+    }
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) {
+        double r = sum[k];
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o, LANES);
+        if (lane == 0) {
+            double res = b[k * ldb + row] - r;
+            if (EPI == EPI_RESID) {
+                out[k * ldo + row] = res;
+            } else {
+                double dn = c2 * dinv[row] * res;
+                if (c1 != 0.0) dn += c1 * d[k * ldd + row];
+                d[k * ldd + row] = dn;
+                out[k * ldo + row] = x[k * ldx + row] + dn;
+            }
+        }
+    }
+}
+
+// first Chebyshev step from a zero guess: d = c2 * dinv * b ; x = d
+template <int NRHS>
+__global__ void k_cheb_first(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
+                             double c2, double* __restrict__ d, double* __restrict__ x, int64_t ldb,
+                             int64_t ldd, int64_t ldx, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double di = dinv[i];
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) {
+        double v = c2 * di * b[k * ldb + i];
+        d[k * ldd + i] = v;
+        x[k * ldx + i] = v;
+    }
+}
+
+template <int NRHS>
+__global__ void k_dense_apply(int n, const double* __restrict__ inv, const double* __restrict__ b,
+                              double* __restrict__ x, int64_t ldb, int64_t ldx, const int* __restrict__ done) {
+    if (done && *done) return;
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double sum[NRHS];
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) sum[k] = 0.0;
+    for (int j = lane; j < n; j += 32) {
+        double a = inv[(int64_t)row * n + j];
+#pragma unroll
+        for (int k = 0; k < NRHS; ++k) sum[k] += a * b[k * ldb + j];
+    }
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) {
+        double r = sum[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) x[k * ldx + row] = r;
+    }
+}
+
+// Y (+)= alpha * M X for NRHS vectors, skipping when done
+template <int LANES, int NRHS>
+__global__ void __launch_bounds__(256)
+k_spmm_plain(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
+             const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+             int64_t ldx, int64_t ldy, double beta, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int lane = threadIdx.x & (LANES - 1);
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    if (row >= nrows) return;
+    const int32_t s = rowptr[row], e = rowptr[row + 1];
+    double sum[NRHS];
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) sum[k] = 0.0;
+    for (int32_t i = s + lane; i < e; i += LANES) {
+        double v = vals[i];
+        int32_t c = cols[i];
+#pragma unroll
+        for (int k = 0; k < NRHS; ++k) sum[k] += v * __ldg(x + k * ldx + c);
+    }
+#pragma unroll
+    for (int k = 0; k < NRHS; ++k) {
+        double r = sum[k];
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o, LANES);
+        if (lane == 0) {
+            double* yp = y + k * ldy + row;
+            *yp = (beta == 0.0) ? r : r + beta * (*yp);
+        }
+    }
+}
+
+// scalar-block matrix with symmetric Dirichlet elimination: out = scale*in, rows/cols of masked
+// nodes zeroed, unit diagonal (apply_symmetric(bc, P), mpetsolver.py:503-504)
+__global__ void __launch_bounds__(256)
+k_masked_copy(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
+              const double* __restrict__ in, double scale, const uint8_t* __restrict__ mask,
+              double* __restrict__ out, double* __restrict__ dinv) {
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+    int lane = threadIdx.x & 7;
+    if (row >= nrows) return;
+    bool rd = mask && mask[row];
+    for (int32_t t = rowptr[row] + lane; t < rowptr[row + 1]; t += 8) {
+        int32_t c = cols[t];
+        double v = scale * in[t];
+        if (rd) v = (c == row) ? 1.0 : 0.0;
+        else if (mask && mask[c]) v = 0.0;
+        out[t] = v;
+        if (c == row) dinv[row] = 1.0 / v;
+    }
+}
+
+__global__ void k_gershgorin(int64_t nrows, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
+                             const double* __restrict__ dinv, double* __restrict__ out) {
+    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    double s = 0;
+    for (int32_t t = rowptr[row]; t < rowptr[row + 1]; ++t) s += fabs(vals[t]);
+    out[row] = s * fabs(dinv[row]);
+}
+
+__global__ void k_scale_by(int64_t n, const double* __restrict__ dinv, double* __restrict__ y) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] *= dinv[i];
+}
+
+// =============================================================================== host CSR tools
+struct HostCsr {
+    int64_t nrows = 0, ncols = 0;
+    std::vector<int32_t> rp, ci;
+    std::vector<double> v;
+    int64_t nnz() const { return (int64_t)ci.size(); }
+};
+
+HostCsr download(const DevCsr& M) {
+    HostCsr H;
+    H.nrows = M.nrows; H.ncols = M.ncols;
+    H.rp.resize(M.nrows + 1); H.ci.resize(M.nnz); H.v.resize(M.nnz);
+    CUDA_CHECK(cudaMemcpy(H.rp.data(), M.rowptr, sizeof(int32_t) * (M.nrows + 1), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(H.ci.data(), M.col, sizeof(int32_t) * M.nnz, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(H.v.data(), M.val, sizeof(double) * M.nnz, cudaMemcpyDeviceToHost));
+    return H;
+}
+
+DevCsr upload(mpet_ctx* ctx, const HostCsr& H) {
+    DevCsr M;
+    M.nrows = H.nrows; M.ncols = H.ncols; M.nnz = H.nnz();
+    M.rowptr = dev_alloc<int32_t>(ctx, H.nrows + 1);
+    M.col = dev_alloc<int32_t>(ctx, M.nnz);
+    M.val = dev_alloc<double>(ctx, M.nnz);
+    CUDA_CHECK(cudaMemcpy(M.rowptr, H.rp.data(), sizeof(int32_t) * (H.nrows + 1), cudaMemcpyHostToDevice));
+    if (M.nnz) {
+        CUDA_CHECK(cudaMemcpy(M.col, H.ci.data(), sizeof(int32_t) * M.nnz, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(M.val, H.v.data(), sizeof(double) * M.nnz, cudaMemcpyHostToDevice));
+    }
+    return M;
+}
+
+HostCsr transpose(const HostCsr& A) {
+    HostCsr T;
+    T.nrows = A.ncols; T.ncols = A.nrows;
+    T.rp.assign(A.ncols + 1, 0);
+    for (int32_t c : A.ci) T.rp[c + 1]++;
+    for (int64_t i = 0; i < A.ncols; ++i) T.rp[i + 1] += T.rp[i];
+    T.ci.resize(A.nnz()); T.v.resize(A.nnz());
+    std::vector<int32_t> pos(T.rp.begin(), T.rp.end() - 1);
+    for (int64_t r = 0; r < A.nrows; ++r)
+        for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t) {
+            int32_t p = pos[A.ci[t]]++;
+            T.ci[p] = (int32_t)r;
+            T.v[p] = A.v[t];
+        }
+    return T;
+}
+
+// C = A * B (Gustavson, dense accumulator), columns sorted per row
+HostCsr spgemm(const HostCsr& A, const HostCsr& B) {
+    HostCsr Cm;
+    Cm.nrows = A.nrows; Cm.ncols = B.ncols;
+    Cm.rp.assign(A.nrows + 1, 0);
+    std::vector<double> acc(B.ncols, 0.0);
+    std::vector<int32_t> marker(B.ncols, -1), list;
+    for (int64_t r = 0; r < A.nrows; ++r) {
+        list.clear();
+        for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t) {
+            int32_t k = A.ci[t];
+            double av = A.v[t];
+            for (int32_t u = B.rp[k]; u < B.rp[k + 1]; ++u) {
+                int32_t c = B.ci[u];
+                if (marker[c] != (int32_t)r) { marker[c] = (int32_t)r; list.push_back(c); acc[c] = 0.0; }
+                acc[c] += av * B.v[u];
+            }
+        }
+        std::sort(list.begin(), list.end());
+        for (int32_t c : list) { Cm.ci.push_back(c); Cm.v.push_back(acc[c]); }
+        Cm.rp[r + 1] = (int32_t)Cm.ci.size();
+    }
+    return Cm;
+}
+
+// Smoothed-aggregation prolongator for an SPD matrix with possible identity (Dirichlet) rows.
+// Returns P (nrows x naggregates); naggregates == 0 means "cannot coarsen".
+HostCsr sa_prolongator(const HostCsr& A, double theta, int64_t& nagg) {
+    const int64_t n = A.nrows;
+    std::vector<double> diag(n, 1.0);
+    for (int64_t r = 0; r < n; ++r)
+        for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t)
+            if (A.ci[t] == r) diag[r] = A.v[t];
+    // strength of connection: |a_ij| >= theta * sqrt(a_ii a_jj)
+    std::vector<int32_t> srp(n + 1, 0), sci;
+    std::vector<double> sval;
+    std::vector<char> isolated(n, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t) {
+            int32_t c = A.ci[t];
+            if (c == r || A.v[t] == 0.0) continue;
+            if (std::fabs(A.v[t]) >= theta * std::sqrt(std::fabs(diag[r] * diag[c]))) {
+                sci.push_back(c);
+                sval.push_back(std::fabs(A.v[t]) / std::sqrt(std::fabs(diag[r] * diag[c])));
+            }
+        }
+        srp[r + 1] = (int32_t)sci.size();
+        bool any_off = false;
+        for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t)
+            if (A.ci[t] != r && A.v[t] != 0.0) { any_off = true; break; }
+        isolated[r] = any_off ? 0 : 1;        // identity rows (eliminated Dirichlet dofs) stay out
+    }
+    std::vector<int32_t> agg(n, -1);
+    nagg = 0;
+    // pass 1: seed aggregates from nodes whose whole strong neighbourhood is free
+    for (int64_t r = 0; r < n; ++r) {
+        if (agg[r] != -1 || isolated[r]) continue;
+        bool free_nb = true;
+        for (int32_t t = srp[r]; t < srp[r + 1]; ++t)
+            if (agg[sci[t]] != -1) { free_nb = false; break; }
+        if (!free_nb || srp[r + 1] == srp[r]) continue;
+        agg[r] = (int32_t)nagg;
+        for (int32_t t = srp[r]; t < srp[r + 1]; ++t) agg[sci[t]] = (int32_t)nagg;
+        nagg++;
+    }
+    // pass 2: attach leftovers to the most strongly connected neighbouring aggregate
+    std::vector<int32_t> agg2(agg);
+    for (int64_t r = 0; r < n; ++r) {
+        if (agg[r] != -1 || isolated[r]) continue;
+        double best = -1; int32_t who = -1;
+        for (int32_t t = srp[r]; t < srp[r + 1]; ++t)
+            if (agg[sci[t]] != -1 && sval[t] > best) { best = sval[t]; who = agg[sci[t]]; }
+        if (who >= 0) agg2[r] = who;
+    }
+    agg.swap(agg2);
+    // pass 3: what is still free forms new aggregates with its free strong neighbours
+    for (int64_t r = 0; r < n; ++r) {
+        if (agg[r] != -1 || isolated[r]) continue;
+        agg[r] = (int32_t)nagg;
+        for (int32_t t = srp[r]; t < srp[r + 1]; ++t)
+            if (agg[sci[t]] == -1 && !isolated[sci[t]]) agg[sci[t]] = (int32_t)nagg;
+        nagg++;
+    }
+    HostCsr P;
+    if (nagg == 0) return P;
+    // tentative prolongator (piecewise constant), then one damped-Jacobi smoothing step
+    HostCsr T;
+    T.nrows = n; T.ncols = nagg;
+    T.rp.assign(n + 1, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        if (agg[r] >= 0) { T.ci.push_back(agg[r]); T.v.push_back(1.0); }
+        T.rp[r + 1] = (int32_t)T.ci.size();
+    }
+    // rho(D^-1 A) by power iteration
+    std::vector<double> x(n), y(n);
+    for (int64_t i = 0; i < n; ++i) x[i] = 1.0 + 0.37 * std::sin(1.7 * (double)i);
+    double rho = 1.0;
+    for (int it = 0; it < 15; ++it) {
+        double nx = 0;
+        for (int64_t i = 0; i < n; ++i) nx += x[i] * x[i];
+        nx = std::sqrt(nx);
+        for (int64_t i = 0; i < n; ++i) x[i] /= nx;
+        for (int64_t r = 0; r < n; ++r) {
+            double s = 0;
+            for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t) s += A.v[t] * x[A.ci[t]];
+            y[r] = s / diag[r];
+        }
+        double ny = 0;
+        for (int64_t i = 0; i < n; ++i) ny += y[i] * y[i];
+        rho = std::sqrt(ny);
+        x.swap(y);
+    }
+    rho *= 1.1;
+    const double omega = (4.0 / 3.0) / rho;
+    // P = (I - omega D^-1 A) T
+    HostCsr AT = spgemm(A, T);
+    P.nrows = n; P.ncols = nagg;
+    P.rp.assign(n + 1, 0);
+    std::vector<std::pair<int32_t, double>> rowbuf;
+    for (int64_t r = 0; r < n; ++r) {
+        if (!isolated[r]) {
+            rowbuf.clear();
+            for (int32_t t = AT.rp[r]; t < AT.rp[r + 1]; ++t)
+                rowbuf.emplace_back(AT.ci[t], -omega / diag[r] * AT.v[t]);
+            if (agg[r] >= 0) rowbuf.emplace_back(agg[r], 1.0);
+            std::sort(rowbuf.begin(), rowbuf.end(),
+                      [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) { return a.first < b.first; });
+            for (size_t q = 0; q < rowbuf.size(); ++q) {
+                if (!P.ci.empty() && (int32_t)P.ci.size() > P.rp[r] && P.ci.back() == rowbuf[q].first)
+                    P.v.back() += rowbuf[q].second;
+                else { P.ci.push_back(rowbuf[q].first); P.v.push_back(rowbuf[q].second); }
+            }
+        }
+        P.rp[r + 1] = (int32_t)P.ci.size();
+    }
+    return P;
+}
+
+std::vector<double> dense_inverse(const HostCsr& A) {
+    const int n = (int)A.nrows;
+    std::vector<double> M((size_t)n * n, 0.0), I((size_t)n * n, 0.0);
+    double tr = 0;
+    for (int r = 0; r < n; ++r) {
+        for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t) M[(size_t)r * n + A.ci[t]] += A.v[t];
+        I[(size_t)r * n + r] = 1.0;
+        tr += std::fabs(M[(size_t)r * n + r]);
+    }
+    const double tiny = 1e-13 * (tr / std::max(1, n));
+    for (int k = 0; k < n; ++k) {   // Gauss-Jordan with partial pivoting
+        int piv = k;
+        for (int r = k + 1; r < n; ++r)
+            if (std::fabs(M[(size_t)r * n + k]) > std::fabs(M[(size_t)piv * n + k])) piv = r;
+        if (piv != k)
+            for (int c = 0; c < n; ++c) {
+                std::swap(M[(size_t)k * n + c], M[(size_t)piv * n + c]);
+                std::swap(I[(size_t)k * n + c], I[(size_t)piv * n + c]);
+            }
+        double p = M[(size_t)k * n + k];
+        if (std::fabs(p) < tiny) p = (p < 0 ? -tiny : tiny);   // singular block (pure Neumann): regularise
+        double ip = 1.0 / p;
+        for (int c = 0; c < n; ++c) { M[(size_t)k * n + c] *= ip; I[(size_t)k * n + c] *= ip; }
+        for (int r = 0; r < n; ++r) {
+            if (r == k) continue;
+            double f = M[(size_t)r * n + k];
+            if (f == 0.0) continue;
+            for (int c = 0; c < n; ++c) {
+                M[(size_t)r * n + c] -= f * M[(size_t)k * n + c];
+                I[(size_t)r * n + c] -= f * I[(size_t)k * n + c];
+            }
+        }
+    }
+    return I;
+}
+
+// =============================================================================== hierarchy
+const int kChebDegree = 2;
+const double kChebRatio = 4.0;    // smooth the upper [lambda_max / ratio, lambda_max] of D^-1 A
+const int64_t kCoarseMax = 300;
+const int kMaxLevels = 12;
+
+template <int NRHS, int EPI>
+void launch_epi(mpet_ctx* ctx, const DevCsr& M, const double* x, const double* b, double* out, double* d,
+                const double* dinv, double c1, double c2, int64_t ldx, int64_t ldb, int64_t ldo, int64_t ldd,
+                const int* done, cudaStream_t st) {
+    double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
+    const int th = 256;
+    if (mean > 20)
+        k_spmm_epi<32, NRHS, EPI><<<grid_for(M.nrows * 32, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, ldx, ldb, ldo, ldd, done);
+    else if (mean > 10)
+        k_spmm_epi<16, NRHS, EPI><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, ldx, ldb, ldo, ldd, done);
+    else
+        k_spmm_epi<8, NRHS, EPI><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, ldx, ldb, ldo, ldd, done);
+    LAUNCH_CHECK(ctx);
+}
+
+template <int NRHS>
+void launch_plain(mpet_ctx* ctx, const DevCsr& M, const double* x, double* y, int64_t ldx, int64_t ldy,
+                  double beta, const int* done, cudaStream_t st) {
+    double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
+    const int th = 256;
+    if (mean > 10)
+        k_spmm_plain<16, NRHS><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, ldx, ldy, beta, done);
+    else if (mean > 3)
+        k_spmm_plain<8, NRHS><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, ldx, ldy, beta, done);
+    else
+        k_spmm_plain<2, NRHS><<<grid_for(M.nrows * 2, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, ldx, ldy, beta, done);
+    LAUNCH_CHECK(ctx);
+}
+
+// Chebyshev smoothing on level L: x_out = S(b, x_in); x_in == nullptr means zero initial guess.
+template <int NRHS>
+void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, int64_t ldb, const double* x_in, int64_t ldxin,
+               double* x_out, int64_t ldxout, const int* done, cudaStream_t st) {
+    const int64_t n = L.A.nrows;
+    const double lmax = L.lambda_max, lmin = lmax / kChebRatio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+    const double sigma = theta / delta;
+    double rho_old = 1.0 / sigma;
+    double* buf[2] = {L.x, L.t};
+    const double* cur = x_in;
+    int64_t ldcur = ldxin;
+    int steps = kChebDegree;
+    for (int k = 0; k < steps; ++k) {
+        bool last = (k == steps - 1);
+        double* dst = last ? x_out : buf[k & 1];
+        int64_t lddst = last ? ldxout : n;
+        bool bounce = last && cur == x_out;    // SpMM cannot run in place
+        if (bounce) { dst = buf[k & 1]; lddst = n; }
+        if (k == 0) {
+            if (cur == nullptr) {
+                k_cheb_first<NRHS><<<grid_for(n, 256), 256, 0, st>>>(n, b, L.dinv, 1.0 / theta, L.r, dst, ldb, n, lddst, done);
+                LAUNCH_CHECK(ctx);
+            } else {
+                launch_epi<NRHS, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, 0.0, 1.0 / theta, ldcur, ldb, lddst, n, done, st);
+            }
+        } else {
+            double rho = 1.0 / (2.0 * sigma - rho_old);
+            launch_epi<NRHS, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, rho * rho_old, 2.0 * rho / delta, ldcur, ldb, lddst, n, done, st);
+            rho_old = rho;
+        }
+        if (bounce) {
+            for (int q = 0; q < NRHS; ++q)
+                CUDA_CHECK(cudaMemcpyAsync(x_out + q * ldxout, dst + q * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        }
+        cur = dst;
+        ldcur = lddst;
+    }
+}
+
+template <int NRHS>
+void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, int64_t ldb, double* x, int64_t ldx,
+            const int* done, cudaStream_t st) {
+    AmgLevel& L = H.levels[lev];
+    const int64_t n = L.A.nrows;
+    if (lev == (int)H.levels.size() - 1) {
+        if (H.coarse_inv) {
+            k_dense_apply<NRHS><<<grid_for((int64_t)n * 32, 256), 256, 0, st>>>((int)n, H.coarse_inv, b, x, ldb, ldx, done);
+            LAUNCH_CHECK(ctx);
+        } else {
+            chebyshev<NRHS>(ctx, L, b, ldb, nullptr, 0, x, ldx, done, st);
+        }
+        return;
+    }
+    AmgLevel& C = H.levels[lev + 1];
+    const int64_t nc = C.A.nrows;
+    // pre-smooth from zero into L.b2 (kept in x), residual, restrict
+    chebyshev<NRHS>(ctx, L, b, ldb, nullptr, 0, x, ldx, done, st);
+    launch_epi<NRHS, EPI_RESID>(ctx, L.A, x, b, L.t, nullptr, nullptr, 0, 0, ldx, ldb, n, 0, done, st);
+    launch_plain<NRHS>(ctx, C.R, L.t, C.b, n, nc, 0.0, done, st);
+    double* xc = C.x + (int64_t)NRHS * nc;   // second half of the coarse x buffer holds the coarse solution
+    vcycle<NRHS>(ctx, H, lev + 1, C.b, nc, xc, nc, done, st);
+    launch_plain<NRHS>(ctx, C.P, xc, x, nc, ldx, 1.0, done, st);
+    // post-smooth in place: x_in = x (copy through the level buffers), final write back to x
+    chebyshev<NRHS>(ctx, L, b, ldb, x, ldx, x, ldx, done, st);
+}
+
+void alloc_level_work(mpet_ctx* ctx, AmgLevel& L, int nrhs) {
+    int64_t n = L.A.nrows;
+    L.x = dev_alloc<double>(ctx, 2 * n * nrhs);   // [0,nrhs*n): ping buffer, [nrhs*n, 2*nrhs*n): coarse solution
+    L.t = dev_alloc<double>(ctx, n * nrhs);
+    L.r = dev_alloc<double>(ctx, n * nrhs);       // Chebyshev direction d
+    L.b = dev_alloc<double>(ctx, n * nrhs);
+}
+
+double estimate_lambda_max(mpet_ctx* ctx, AmgLevel& L, cudaStream_t st) {
+    // Gershgorin bound on D^-1 A caps a power-iteration estimate
+    const int64_t n = L.A.nrows;
+    double* tmp = nullptr;
+    CUDA_CHECK(cudaMalloc(&tmp, sizeof(double) * n));
+    k_gershgorin<<<grid_for(n, 256), 256, 0, st>>>(n, L.A.rowptr, L.A.val, L.dinv, tmp);
+    LAUNCH_CHECK(ctx);
+    std::vector<double> h(n);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    double gersh = 0;
+    for (double v : h) gersh = std::max(gersh, v);
+    // power iteration on device
+    std::vector<double> x0(n);
+    for (int64_t i = 0; i < n; ++i) x0[i] = 1.0 + 0.5 * std::sin(0.37 * (double)i + 0.1 * (double)(i % 7));
+    double* x = nullptr; double* y = nullptr;
+    CUDA_CHECK(cudaMalloc(&x, sizeof(double) * n));
+    CUDA_CHECK(cudaMalloc(&y, sizeof(double) * n));
+    CUDA_CHECK(cudaMemcpy(x, x0.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    double lam = 0;
+    for (int it = 0; it < 20; ++it) {
+        launch_plain<1>(ctx, L.A, x, y, n, n, 0.0, nullptr, st);
+        k_scale_by<<<grid_for(n, 256), 256, 0, st>>>(n, L.dinv, y);
+        LAUNCH_CHECK(ctx);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), y, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        double ny = 0;
+        for (double v : h) ny += v * v;
+        ny = std::sqrt(ny);
+        lam = ny;   // x is normalised
+        if (ny == 0) break;
+        for (double& v : h) v /= ny;
+        CUDA_CHECK(cudaMemcpy(x, h.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    cudaFree(tmp); cudaFree(x); cudaFree(y);
+    double est = 1.1 * lam;
+    if (est <= 0 || est > gersh) est = gersh;
+    return est;
+}
+
+void compute_dinv_host(mpet_ctx* ctx, AmgLevel& L, const HostCsr& H) {
+    std::vector<double> d(H.nrows, 1.0);
+    for (int64_t r = 0; r < H.nrows; ++r)
+        for (int32_t t = H.rp[r]; t < H.rp[r + 1]; ++t)
+            if (H.ci[t] == r && H.v[t] != 0.0) d[r] = 1.0 / H.v[t];
+    L.dinv = dev_alloc<double>(ctx, H.nrows);
+    CUDA_CHECK(cudaMemcpy(L.dinv, d.data(), sizeof(double) * H.nrows, cudaMemcpyHostToDevice));
+}
+
+// extend H below its current last level (whose A is on device) by smoothed aggregation
+void extend_by_aggregation(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    HostCsr A = download(H.levels.back().A);
+    double theta = 0.08;
+    while (A.nrows > kCoarseMax && (int)H.levels.size() < kMaxLevels) {
+        int64_t nagg = 0;
+        HostCsr P = sa_prolongator(A, theta, nagg);
+        if (nagg == 0 || nagg > 0.8 * A.nrows) break;
+        HostCsr R = transpose(P);
+        HostCsr Ac = spgemm(R, spgemm(A, P));
+        AmgLevel L;
+        L.A = upload(ctx, Ac);
+        L.P = upload(ctx, P);
+        L.R = upload(ctx, R);
+        compute_dinv_host(ctx, L, Ac);
+        H.levels.push_back(L);
+        A = std::move(Ac);
+        theta *= 0.5;
+    }
+    if (A.nrows <= 700) {
+        std::vector<double> inv = dense_inverse(A);
+        H.coarse_n = A.nrows;
+        H.coarse_inv = dev_alloc<double>(ctx, (int64_t)inv.size());
+        CUDA_CHECK(cudaMemcpy(H.coarse_inv, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice));
+    }
+}
+
+void finish_hierarchy(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
+    for (auto& L : H.levels) {
+        alloc_level_work(ctx, L, H.nrhs);
+        L.lambda_max = estimate_lambda_max(ctx, L, st);
+    }
+}
+
+DevCsr masked_block(mpet_ctx* ctx, const NodeGraph& g, const double* vals, double scale, const uint8_t* mask,
+                    double** dinv_out, cudaStream_t st) {
+    DevCsr M;
+    M.nrows = g.nrows; M.ncols = g.ncols; M.nnz = g.nnz;
+    M.rowptr = g.rowptr; M.col = g.col;
+    M.val = dev_alloc<double>(ctx, g.nnz);
+    *dinv_out = dev_alloc<double>(ctx, g.nrows);
+    k_masked_copy<<<grid_for(g.nrows * 8, 256), 256, 0, st>>>(g.nrows, g.rowptr, g.col, vals, scale, mask, M.val, *dinv_out);
+    LAUNCH_CHECK(ctx);
+    return M;
+}
+
+// P2 -> P1 embedding (rows: P2 nodes, cols: vertices); Dirichlet rows/cols dropped
+HostCsr p2_to_p1(int64_t nv, int64_t ne, const std::vector<int32_t>& edge_v, const std::vector<uint8_t>& mask2) {
+    HostCsr P;
+    P.nrows = nv + ne; P.ncols = nv;
+    P.rp.assign(P.nrows + 1, 0);
+    for (int64_t r = 0; r < P.nrows; ++r) {
+        if (!mask2[r]) {
+            if (r < nv) { P.ci.push_back((int32_t)r); P.v.push_back(1.0); }
+            else {
+                int32_t a = edge_v[2 * (r - nv)], b = edge_v[2 * (r - nv) + 1];
+                if (!mask2[a]) { P.ci.push_back(a); P.v.push_back(0.5); }
+                if (!mask2[b]) { P.ci.push_back(b); P.v.push_back(0.5); }
+            }
+        }
+        P.rp[r + 1] = (int32_t)P.ci.size();
+    }
+    return P;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------- public
+void amg_free(mpet_ctx* ctx) {
+    for (void* p : ctx->amg_allocs) cudaFree(p);
+    ctx->amg_allocs.clear();
+    delete ctx->amg_u;
+    ctx->amg_u = nullptr;
+    for (int i = 0; i < MPET_MAX_NETWORKS; ++i) { delete ctx->amg_p[i]; ctx->amg_p[i] = nullptr; }
+}
+
+void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
+    MPET_REQUIRE(ctx->prec_ready, "mpet_assemble_prec must run before mpet_pc_setup");
+    amg_free(ctx);                    // a new dt / new Dirichlet set rebuilds the hierarchies
+    struct ArenaGuard {
+        mpet_ctx* c;
+        explicit ArenaGuard(mpet_ctx* c_) : c(c_) { c->arena = &c->amg_allocs; }
+        ~ArenaGuard() { c->arena = nullptr; }
+    } guard(ctx);
+    const int64_t n2 = ctx->N2, nv = ctx->Nv;
+    const int A = ctx->A;
+    if (!ctx->bc_mask) {
+        ctx->bc_mask = dev_alloc<uint8_t>(ctx, ctx->N);
+        CUDA_CHECK(cudaMemsetAsync(ctx->bc_mask, 0, ctx->N, st));
+    }
+    // the three displacement components must share their Dirichlet set to share one hierarchy
+    std::vector<uint8_t> hmask(ctx->N);
+    CUDA_CHECK(cudaMemcpyAsync(hmask.data(), ctx->bc_mask, ctx->N, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int k = 1; k < 3; ++k)
+        MPET_REQUIRE(std::equal(hmask.begin(), hmask.begin() + n2, hmask.begin() + k * n2),
+                     "displacement components carry different Dirichlet sets (not supported by the shared block)");
+    std::vector<uint8_t> mask2(hmask.begin(), hmask.begin() + n2);
+    std::vector<int32_t> edge_v(2 * ctx->Ne);
+    CUDA_CHECK(cudaMemcpy(edge_v.data(), ctx->edge_v, sizeof(int32_t) * 2 * ctx->Ne, cudaMemcpyDeviceToHost));
+
+    // ---- displacement block
+    {
+        AmgHierarchy* H = new AmgHierarchy();
+        H->nrhs = 3;
+        AmgLevel L0;
+        L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->mu, ctx->bc_mask, &L0.dinv, st);
+        H->levels.push_back(L0);
+        AmgLevel L1;
+        L1.A = masked_block(ctx, ctx->g11, ctx->l11, ctx->mu, ctx->bc_mask /* vertices are the first Nv nodes */,
+                            &L1.dinv, st);
+        HostCsr P = p2_to_p1(nv, ctx->Ne, edge_v, mask2);
+        L1.P = upload(ctx, P);
+        L1.R = upload(ctx, transpose(P));
+        H->levels.push_back(L1);
+        extend_by_aggregation(ctx, *H, st);
+        finish_hierarchy(ctx, *H, st);
+        ctx->amg_u = H;
+    }
+    // ---- pressure blocks
+    for (int i = 0; i < A; ++i) {
+        AmgHierarchy* H = new AmgHierarchy();
+        H->nrhs = 1;
+        AmgLevel L0;
+        L0.A = masked_block(ctx, ctx->g11, ctx->pp11 + (int64_t)i * ctx->g11.nnz, 1.0,
+                            ctx->bc_mask + 3 * n2 + (int64_t)i * nv, &L0.dinv, st);
+        H->levels.push_back(L0);
+        extend_by_aggregation(ctx, *H, st);
+        finish_hierarchy(ctx, *H, st);
+        ctx->amg_p[i] = H;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
+    const int64_t n2 = ctx->N2, nv = ctx->Nv;
+    vcycle<3>(ctx, *ctx->amg_u, 0, r, n2, z, n2, done, st);
+    for (int i = 0; i < ctx->A; ++i) {
+        int64_t off = 3 * n2 + (int64_t)i * nv;
+        vcycle<1>(ctx, *ctx->amg_p[i], 0, r + off, nv, z + off, nv, done, st);
+    }
+}
+
+int amg_num_levels(mpet_ctx* ctx, int block) {
+    AmgHierarchy* H = block == 0 ? ctx->amg_u : ctx->amg_p[block - 1];
+    return H ? (int)H->levels.size() : 0;
+}

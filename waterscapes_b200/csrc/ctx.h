@@ -79,6 +79,8 @@ struct mpet_ctx {
     int64_t launches = 0;
     int64_t bytes = 0;
     std::vector<void*> allocs;
+    std::vector<void*> amg_allocs;          // freed and rebuilt by every mpet_pc_setup
+    std::vector<void*>* arena = nullptr;    // when set, dev_alloc records here instead of allocs
     int sm_count = 148;
 
     // mesh / space
@@ -129,7 +131,7 @@ T* dev_alloc(mpet_ctx* ctx, int64_t n) {
     if (n <= 0) n = 1;
     void* p = nullptr;
     CUDA_CHECK(cudaMalloc(&p, (size_t)n * sizeof(T)));
-    ctx->allocs.push_back(p);
+    (ctx->arena ? *ctx->arena : ctx->allocs).push_back(p);
     ctx->bytes += n * (int64_t)sizeof(T);
     return (T*)p;
 }
@@ -167,9 +169,13 @@ void compute_geometry(mpet_ctx* ctx, cudaStream_t st);
 void assemble_lhs(mpet_ctx* ctx, cudaStream_t st);
 void assemble_prec(mpet_ctx* ctx, cudaStream_t st);
 void ensure_m22(mpet_ctx* ctx, cudaStream_t st);
+// amg.cu
+void amg_setup(mpet_ctx* ctx, cudaStream_t st);
+void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st);
+void amg_free(mpet_ctx* ctx);
 // spmv.cu
 void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
               const double* vals, const double* x, double* y, double beta, const uint8_t* rowmask,
-              cudaStream_t st);
+              cudaStream_t st, const int* done = nullptr);
 void csr32_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, double* y, int64_t ldy,
                 int nrhs, double alpha, double beta, cudaStream_t st);

@@ -1,8 +1,516 @@
+// Preconditioned Krylov solvers on device: MINRES (symmetric S) and restarted GMRES (any S).
+//
+// Replaces PETScKrylovSolver("minres", "hypre_amg").solve (mpetsolver.py:507,553-556;
+// mpettotalpressuresolver.py:448,492-493) and -- run to a tight tolerance -- the LUSolver path
+// (mpetsolver.py:347,379,422,456).  Algorithm = PETSc's KSPMINRES recurrence (one operator and one
+// preconditioner application per iteration, convergence on the preconditioned norm |eta|).
+//
+// Dirichlet conditions are imposed the way apply_symmetric(bc, A, b) does (bc_symmetric.py:11-22)
+// without ever touching A: the initial guess carries the boundary values, the initial residual is
+// zero on Dirichlet rows, and the operator returns identity on those rows (spmv.cu row mask).  All
+// Krylov vectors then stay exactly zero there, so columns need no masking.
+//
+// All scalars (Lanczos coefficients, Givens rotations, convergence flag) live in device memory and
+// are updated by single-thread kernels, so the host enqueues iterations without synchronising; once
+// the `done` flag is set every later kernel returns immediately.  Reductions are two-stage with a
+// fixed block count and fixed summation order (bit-reproducible).
 #include "ctx.h"
-void krylov_free(mpet_ctx*) {}
-void krylov_solve(mpet_ctx* ctx, const double*, double*, double*, cudaStream_t) { MPET_REQUIRE(false, "krylov: not implemented"); }
-void pc_setup(mpet_ctx* ctx, cudaStream_t) { MPET_REQUIRE(false, "pc: not implemented"); }
-void pc_apply(mpet_ctx* ctx, const double*, double*, cudaStream_t) { MPET_REQUIRE(false, "pc: not implemented"); }
-void amg_free(mpet_ctx*) {}
-void dist_attach(mpet_ctx* ctx, const void*, int, int) { MPET_REQUIRE(false, "dist: not implemented"); }
+#include <cmath>
+#include <vector>
+
+void scatter_bc_values(mpet_ctx* ctx, double* out, cudaStream_t st);   // rhs.cu
+
+namespace {
+
+const int kRedBlocks = 1184;   // 148 SMs x 8
+const int kRedThreads = 256;
+
+enum {
+    S_BETA = 0, S_BETA_OLD, S_ETA, S_C, S_C_OLD, S_S, S_S_OLD, S_ALPHA, S_RHO1, S_RHO2, S_RHO3, S_CETA,
+    S_NORM, S_NORM0, S_TOL, S_DP, S_COUNT = 32
+};
+enum { F_DONE = 0, F_CONV, F_ITERS, F_MAXIT, F_BREAKDOWN, F_PENDING, F_COUNT = 8 };
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    int nw = blockDim.x >> 5;
+    v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    __syncthreads();
+    return v;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+              double* __restrict__ partials, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += a[i] * b[i];
+    s = block_reduce_sum(s, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// sum of kRedBlocks partials in a fixed order by one block
+__device__ double final_sum(const double* __restrict__ partials, int nparts, double* sm) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partials[i];
+    return block_reduce_sum(s, sm);
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_final_store(const double* __restrict__ partials, int nparts, double* __restrict__ out) {
+    __shared__ double sm[32];
+    double s = final_sum(partials, nparts, sm);
+    if (threadIdx.x == 0) *out = s;
+}
+
+// r = mask ? 0 : b - y
+__global__ void k_residual(const double* __restrict__ b, const double* __restrict__ y,
+                           const uint8_t* __restrict__ mask, int64_t n, double* __restrict__ r) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) r[i] = (mask && mask[i]) ? 0.0 : b[i] - y[i];
+}
+
+__global__ void k_jacobi(const double* __restrict__ dinv, const double* __restrict__ r, int64_t n,
+                         double* __restrict__ z, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) z[i] = dinv[i] * r[i];
+}
+
+__global__ void k_abs_diag_inv(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
+                               const double* __restrict__ vals, const uint8_t* __restrict__ mask,
+                               double* __restrict__ dinv) {
+    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    if (mask && mask[row]) { dinv[row] = 1.0; return; }
+    int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (cols[mid] < (int32_t)row) lo = mid + 1; else hi = mid;
+    }
+    double d = vals[lo];
+    dinv[row] = (d != 0.0) ? 1.0 / fabs(d) : 1.0;
+}
+
+// ---------------------------------------------------------------------------------- MINRES
+__global__ void __launch_bounds__(kRedThreads)
+k_minres_init(const double* __restrict__ partials, int nparts, double rtol, double atol, int maxit,
+              double* __restrict__ sc, int* __restrict__ fl) {
+    __shared__ double sm[32];
+    double dp = final_sum(partials, nparts, sm);
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < S_COUNT; ++i) sc[i] = 0.0;
+    for (int i = 0; i < F_COUNT; ++i) fl[i] = 0;
+    fl[F_MAXIT] = maxit;
+    if (dp < 0.0) { fl[F_BREAKDOWN] = 1; fl[F_DONE] = 1; return; }   // indefinite preconditioner
+    double beta = sqrt(dp);
+    sc[S_BETA] = beta; sc[S_ETA] = beta; sc[S_C] = 1.0; sc[S_C_OLD] = 1.0;
+    sc[S_NORM] = beta; sc[S_NORM0] = beta;
+    sc[S_TOL] = fmax(rtol * beta, atol);
+    if (beta <= sc[S_TOL] || beta == 0.0) { fl[F_CONV] = 1; fl[F_DONE] = 1; }
+}
+
+__global__ void k_minres_start(int64_t n, const double* __restrict__ sc, const double* __restrict__ r,
+                               const double* __restrict__ z, double* __restrict__ v, double* __restrict__ u,
+                               double* __restrict__ v_old, double* __restrict__ u_old, double* __restrict__ w1,
+                               double* __restrict__ w2, const int* __restrict__ done) {
+    if (*done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ib = 1.0 / sc[S_BETA];
+    v[i] = r[i] * ib; u[i] = z[i] * ib;
+    v_old[i] = 0.0; u_old[i] = 0.0; w1[i] = 0.0; w2[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_minres_alpha(const double* __restrict__ partials, int nparts, double* __restrict__ sc,
+               const int* __restrict__ fl) {
+    if (fl[F_DONE]) return;
+    __shared__ double sm[32];
+    double a = final_sum(partials, nparts, sm);
+    if (threadIdx.x == 0) sc[S_ALPHA] = a;
+}
+
+// r -= alpha v + beta v_old ; z -= alpha u + beta u_old ; partial(r.z)
+__global__ void __launch_bounds__(kRedThreads)
+k_minres_update(int64_t n, const double* __restrict__ sc, const double* __restrict__ v,
+                const double* __restrict__ v_old, const double* __restrict__ u,
+                const double* __restrict__ u_old, double* __restrict__ r, double* __restrict__ z,
+                double* __restrict__ partials, const int* __restrict__ done) {
+    if (*done) return;
+    __shared__ double sm[32];
+    const double alpha = sc[S_ALPHA], beta = sc[S_BETA];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double ri = r[i] - alpha * v[i] - beta * v_old[i];
+        double zi = z[i] - alpha * u[i] - beta * u_old[i];
+        r[i] = ri; z[i] = zi;
+        s += ri * zi;
+    }
+    s = block_reduce_sum(s, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_minres_rotate(const double* __restrict__ partials, int nparts, double* __restrict__ sc, int* __restrict__ fl) {
+    if (fl[F_DONE]) return;
+    __shared__ double sm[32];
+    double dp = final_sum(partials, nparts, sm);
+    if (threadIdx.x != 0) return;
+    if (dp < 0.0) {
+        // tolerate round-off-sized negatives (exact convergence), flag real indefiniteness
+        if (-dp > 1e-12 * sc[S_NORM0] * sc[S_NORM0]) fl[F_BREAKDOWN] = 1;
+        dp = 0.0;
+    }
+    double beta_old = sc[S_BETA];
+    double beta = sqrt(dp);
+    double alpha = sc[S_ALPHA];
+    double c_oold = sc[S_C_OLD], c_old = sc[S_C], s_oold = sc[S_S_OLD], s_old = sc[S_S];
+    double rho0 = c_old * alpha - c_oold * s_old * beta_old;
+    double rho1 = sqrt(rho0 * rho0 + beta * beta);
+    double rho2 = s_old * alpha + c_oold * c_old * beta_old;
+    double rho3 = s_oold * beta_old;
+    if (rho1 == 0.0) { fl[F_BREAKDOWN] = 1; fl[F_CONV] = 0; fl[F_DONE] = 1; return; }
+    double c = rho0 / rho1, s = beta / rho1;
+    double eta = sc[S_ETA];
+    sc[S_C_OLD] = c_old; sc[S_S_OLD] = s_old; sc[S_C] = c; sc[S_S] = s;
+    sc[S_RHO1] = rho1; sc[S_RHO2] = rho2; sc[S_RHO3] = rho3;
+    sc[S_CETA] = c * eta;
+    sc[S_ETA] = -s * eta;
+    sc[S_BETA_OLD] = beta_old; sc[S_BETA] = beta;
+    sc[S_NORM] = fabs(sc[S_ETA]);
+    sc[S_DP] = dp;
+    int it = fl[F_ITERS] + 1;
+    fl[F_ITERS] = it;
+    if (sc[S_NORM] <= sc[S_TOL]) fl[F_CONV] = 1;
+    if (fl[F_CONV] || it >= fl[F_MAXIT] || beta == 0.0 || fl[F_BREAKDOWN]) fl[F_PENDING] = 1;
+}
+
+// w = (u - rho2 w1 - rho3 w2) / rho1 ; x += c*eta*w ; shift Lanczos vectors
+__global__ void k_minres_finalize(int64_t n, const double* __restrict__ sc, double* __restrict__ x,
+                                  double* __restrict__ w1, double* __restrict__ w2, double* __restrict__ v,
+                                  double* __restrict__ v_old, double* __restrict__ u, double* __restrict__ u_old,
+                                  const double* __restrict__ r, const double* __restrict__ z,
+                                  const int* __restrict__ done) {
+    if (*done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double irho1 = 1.0 / sc[S_RHO1], rho2 = sc[S_RHO2], rho3 = sc[S_RHO3], ceta = sc[S_CETA];
+    const double beta = sc[S_BETA];
+    const double ib = beta != 0.0 ? 1.0 / beta : 0.0;
+    double ui = u[i], w1i = w1[i];
+    double wn = (ui - rho2 * w1i - rho3 * w2[i]) * irho1;
+    w2[i] = w1i; w1[i] = wn;
+    x[i] += ceta * wn;
+    v_old[i] = v[i]; v[i] = r[i] * ib;
+    u_old[i] = ui;   u[i] = z[i] * ib;
+}
+
+__global__ void k_commit(int* __restrict__ fl) {
+    if (fl[F_PENDING]) fl[F_DONE] = 1;
+}
+
+// ---------------------------------------------------------------------------------- GMRES helpers
+template <int NV>
+__global__ void __launch_bounds__(kRedThreads)
+k_multidot(const double* __restrict__ V, int64_t ldv, const double* __restrict__ w, int64_t n,
+           double* __restrict__ partials /* [NV][gridDim] */) {
+    __shared__ double sm[32];
+    double s[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s[k] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double wi = w[i];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s[k] += V[k * ldv + i] * wi;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double r = block_reduce_sum(s[k], sm);
+        if (threadIdx.x == 0) partials[k * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_multifinal(const double* __restrict__ partials, int nparts, double* __restrict__ out, int accumulate) {
+    __shared__ double sm[32];
+    double s = final_sum(partials + (int64_t)blockIdx.x * nparts, nparts, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = accumulate ? out[blockIdx.x] + s : s;
+}
+
+// w -= sum_k h[k] V[k]   (h on device)
+__global__ void k_multi_axpy(const double* __restrict__ V, int64_t ldv, int nv, const double* __restrict__ h,
+                             double sign, int64_t n, double* __restrict__ w) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = w[i];
+    for (int k = 0; k < nv; ++k) acc += sign * h[k] * V[k * ldv + i];
+    w[i] = acc;
+}
+
+__global__ void k_scale_copy(const double* __restrict__ src, double scale, int64_t n, double* __restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] * scale;
+}
+
+}  // namespace
+
+struct KrylovWork {
+    int64_t n = 0;
+    double *r = nullptr, *z = nullptr, *v = nullptr, *v_old = nullptr, *u = nullptr, *u_old = nullptr,
+           *w1 = nullptr, *w2 = nullptr, *partials = nullptr, *sc = nullptr;
+    int* fl = nullptr;
+    double* basis = nullptr;   // GMRES: (restart + 1) vectors
+    int basis_m = 0;
+    double* hdev = nullptr;
+    double* h_sc = nullptr;    // pinned mirrors
+    int* h_fl = nullptr;
+};
+
+static KrylovWork* get_work(mpet_ctx* ctx) {
+    if (ctx->kw && ctx->kw->n == ctx->N) return ctx->kw;
+    MPET_REQUIRE(ctx->kw == nullptr, "context size changed");
+    KrylovWork* k = new KrylovWork();
+    k->n = ctx->N;
+    double** vecs[] = {&k->r, &k->z, &k->v, &k->v_old, &k->u, &k->u_old, &k->w1, &k->w2};
+    for (auto p : vecs) *p = dev_alloc<double>(ctx, ctx->N);
+    k->partials = dev_alloc<double>(ctx, (int64_t)kRedBlocks * 8);
+    k->sc = dev_alloc<double>(ctx, S_COUNT);
+    k->fl = dev_alloc<int>(ctx, F_COUNT);
+    k->hdev = dev_alloc<double>(ctx, 256);
+    CUDA_CHECK(cudaMallocHost(&k->h_sc, sizeof(double) * S_COUNT));
+    CUDA_CHECK(cudaMallocHost(&k->h_fl, sizeof(int) * F_COUNT));
+    ctx->kw = k;
+    return k;
+}
+
+void krylov_free(mpet_ctx* ctx) {
+    if (!ctx->kw) return;
+    cudaFreeHost(ctx->kw->h_sc);
+    cudaFreeHost(ctx->kw->h_fl);
+    delete ctx->kw;
+    ctx->kw = nullptr;
+}
+
+void pc_setup(mpet_ctx* ctx, cudaStream_t st) {
+    MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run before mpet_pc_setup");
+    if (ctx->pc == 1) {
+        if (!ctx->jac_dinv) ctx->jac_dinv = dev_alloc<double>(ctx, ctx->N);
+        k_abs_diag_inv<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N, ctx->rowptr, ctx->cols, ctx->vals,
+                                                              ctx->bc_mask, ctx->jac_dinv);
+        LAUNCH_CHECK(ctx);
+    } else if (ctx->pc == 2) {
+        amg_setup(ctx, st);
+    }
+}
+
+static void pc_apply_flag(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
+    const int64_t n = ctx->N;
+    if (ctx->pc == 0) {
+        CUDA_CHECK(cudaMemcpyAsync(z, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    } else if (ctx->pc == 1) {
+        MPET_REQUIRE(ctx->jac_dinv, "mpet_pc_setup must run before solving with pc = Jacobi");
+        k_jacobi<<<grid_for(n, 256), 256, 0, st>>>(ctx->jac_dinv, r, n, z, done);
+        LAUNCH_CHECK(ctx);
+    } else {
+        MPET_REQUIRE(ctx->amg_u, "mpet_pc_setup must run before solving with pc = AMG");
+        amg_apply(ctx, r, z, done, st);
+    }
+}
+
+void pc_apply(mpet_ctx* ctx, const double* r, double* z, cudaStream_t st) { pc_apply_flag(ctx, r, z, nullptr, st); }
+
+static void dot_to(mpet_ctx* ctx, KrylovWork* k, const double* a, const double* b, const int* done, cudaStream_t st) {
+    k_dot_partial<<<kRedBlocks, kRedThreads, 0, st>>>(a, b, k->n, k->partials, done);
+    LAUNCH_CHECK(ctx);
+}
+
+static void initial_residual(mpet_ctx* ctx, KrylovWork* k, const double* b, double* x, cudaStream_t st) {
+    // x carries the Dirichlet values; r = b - A x on free rows, 0 on Dirichlet rows
+    if (ctx->n_bc > 0) {
+        scatter_bc_values(ctx, x, st);
+    }
+    csr_spmv(ctx, ctx->N, ctx->rowptr, ctx->cols, ctx->vals, x, k->v, 0.0, nullptr, st);
+    k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(b, k->v, ctx->n_bc > 0 ? ctx->bc_mask : nullptr, k->n, k->r);
+    LAUNCH_CHECK(ctx);
+}
+
+static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
+    KrylovWork* k = get_work(ctx);
+    const int64_t n = k->n;
+    const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask : nullptr;
+    initial_residual(ctx, k, b, x, st);
+    pc_apply_flag(ctx, k->r, k->z, nullptr, st);
+    dot_to(ctx, k, k->r, k->z, nullptr, st);
+    k_minres_init<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, ctx->rtol, ctx->atol, ctx->maxit, k->sc, k->fl);
+    LAUNCH_CHECK(ctx);
+    const int* done = k->fl + F_DONE;
+    k_minres_start<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->r, k->z, k->v, k->u, k->v_old, k->u_old, k->w1,
+                                                     k->w2, done);
+    LAUNCH_CHECK(ctx);
+    const int check_every = 5;
+    int enq = 0;
+    while (true) {
+        for (int q = 0; q < check_every && enq < ctx->maxit; ++q, ++enq) {
+            csr_spmv(ctx, n, ctx->rowptr, ctx->cols, ctx->vals, k->u, k->r, 0.0, mask, st, done);
+            dot_to(ctx, k, k->r, k->u, done, st);
+            k_minres_alpha<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
+            LAUNCH_CHECK(ctx);
+            pc_apply_flag(ctx, k->r, k->z, done, st);
+            k_minres_update<<<kRedBlocks, kRedThreads, 0, st>>>(n, k->sc, k->v, k->v_old, k->u, k->u_old, k->r,
+                                                                k->z, k->partials, done);
+            LAUNCH_CHECK(ctx);
+            k_minres_rotate<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
+            LAUNCH_CHECK(ctx);
+            k_minres_finalize<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, x, k->w1, k->w2, k->v, k->v_old, k->u,
+                                                                k->u_old, k->r, k->z, done);
+            LAUNCH_CHECK(ctx);
+            k_commit<<<1, 1, 0, st>>>(k->fl);
+            LAUNCH_CHECK(ctx);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(k->h_fl, k->fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(k->h_sc, k->sc, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (k->h_fl[F_DONE] || enq >= ctx->maxit) break;
+    }
+    info[0] = (double)k->h_fl[F_ITERS];
+    info[1] = (double)k->h_fl[F_CONV];
+    info[2] = k->h_sc[S_NORM0] > 0 ? k->h_sc[S_NORM] / k->h_sc[S_NORM0] : 0.0;
+    info[3] = k->h_sc[S_NORM0];
+    info[4] = (double)k->h_fl[F_BREAKDOWN];
+}
+
+// ---------------------------------------------------------------------------------- GMRES(m)
+static void multidot(mpet_ctx* ctx, KrylovWork* k, const double* V, int nv, const double* w, double* hdev,
+                     int accumulate, cudaStream_t st) {
+    const int G = 296;
+    for (int k0 = 0; k0 < nv; k0 += 4) {
+        int c = std::min(4, nv - k0);
+        const double* Vk = V + (int64_t)k0 * k->n;
+        switch (c) {
+            case 1: k_multidot<1><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
+            case 2: k_multidot<2><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
+            case 3: k_multidot<3><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
+            default: k_multidot<4><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
+        }
+        LAUNCH_CHECK(ctx);
+        k_multifinal<<<c, kRedThreads, 0, st>>>(k->partials, G, hdev + k0, accumulate);
+        LAUNCH_CHECK(ctx);
+    }
+}
+
+static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
+    KrylovWork* k = get_work(ctx);
+    const int64_t n = k->n;
+    const int m = ctx->restart;
+    MPET_REQUIRE(m >= 1 && m <= 120, "GMRES restart must be in 1..120");
+    if (k->basis_m < m) {
+        k->basis = dev_alloc<double>(ctx, (int64_t)(m + 1) * n);
+        k->basis_m = m;
+    }
+    const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask : nullptr;
+    double* V = k->basis;
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
+    int iters = 0;
+    bool converged = false;
+    double norm0 = -1, norm = 0, tol = 0;
+    while (!converged && iters < ctx->maxit) {
+        initial_residual(ctx, k, b, x, st);
+        pc_apply_flag(ctx, k->r, k->z, nullptr, st);
+        dot_to(ctx, k, k->z, k->z, nullptr, st);
+        k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev);
+        LAUNCH_CHECK(ctx);
+        double bb = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&bb, k->hdev, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        double beta = std::sqrt(bb);
+        if (norm0 < 0) { norm0 = beta; tol = std::max(ctx->rtol * norm0, ctx->atol); }
+        norm = beta;
+        if (beta <= tol || beta == 0.0) { converged = true; break; }
+        k_scale_copy<<<grid_for(n, 256), 256, 0, st>>>(k->z, 1.0 / beta, n, V);
+        LAUNCH_CHECK(ctx);
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int j = 0;
+        for (; j < m && iters < ctx->maxit; ++j) {
+            double* w = V + (int64_t)(j + 1) * n;
+            csr_spmv(ctx, n, ctx->rowptr, ctx->cols, ctx->vals, V + (int64_t)j * n, k->r, 0.0, mask, st);
+            pc_apply_flag(ctx, k->r, w, nullptr, st);
+            // classical Gram-Schmidt, two passes (CGS2)
+            multidot(ctx, k, V, j + 1, w, k->hdev, 0, st);
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, j + 1, k->hdev, -1.0, n, w);
+            LAUNCH_CHECK(ctx);
+            multidot(ctx, k, V, j + 1, w, k->hdev + 128, 0, st);
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, j + 1, k->hdev + 128, -1.0, n, w);
+            LAUNCH_CHECK(ctx);
+            dot_to(ctx, k, w, w, nullptr, st);
+            k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev + j + 1);
+            LAUNCH_CHECK(ctx);
+            std::vector<double> h1(j + 2), h2(j + 1);
+            CUDA_CHECK(cudaMemcpyAsync(h1.data(), k->hdev, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(h2.data(), k->hdev + 128, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            for (int i = 0; i <= j; ++i) hcol[i] = h1[i] + h2[i];
+            double hn = std::sqrt(std::max(0.0, h1[j + 1]));
+            hcol[j + 1] = hn;
+            if (hn > 0) {
+                k_scale_copy<<<grid_for(n, 256), 256, 0, st>>>(w, 1.0 / hn, n, w);
+                LAUNCH_CHECK(ctx);
+            }
+            for (int i = 0; i < j; ++i) {   // previous rotations
+                double t = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
+                hcol[i + 1] = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
+                hcol[i] = t;
+            }
+            double den = std::hypot(hcol[j], hcol[j + 1]);
+            cs[j] = den > 0 ? hcol[j] / den : 1.0;
+            sn[j] = den > 0 ? hcol[j + 1] / den : 0.0;
+            hcol[j] = den;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
+            ++iters;
+            norm = std::fabs(g[j + 1]);
+            if (norm <= tol || hn == 0.0) { converged = norm <= tol; ++j; break; }
+        }
+        // solve the triangular system and update x
+        int jj = j;
+        for (int i = jj - 1; i >= 0; --i) {
+            double s = g[i];
+            for (int q = i + 1; q < jj; ++q) s -= H[(size_t)i * m + q] * y[q];
+            y[i] = s / H[(size_t)i * m + i];
+        }
+        if (jj > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(k->hdev, y.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, st));
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, jj, k->hdev, 1.0, n, x);
+            LAUNCH_CHECK(ctx);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        if (jj == 0) break;
+    }
+    info[0] = iters;
+    info[1] = converged ? 1.0 : 0.0;
+    info[2] = norm0 > 0 ? norm / norm0 : 0.0;
+    info[3] = norm0 < 0 ? 0.0 : norm0;
+    info[4] = 0.0;
+}
+
+void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
+    MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run before mpet_solve");
+    for (int i = 0; i < 8; ++i) info[i] = 0.0;
+    if (ctx->method == 0) minres(ctx, b, x, info, st);
+    else gmres(ctx, b, x, info, st);
+}
+
+void dist_attach(mpet_ctx* ctx, const void*, int, int) { MPET_REQUIRE(false, "multi-GPU attach: not built yet"); }
 void dist_free(mpet_ctx*) {}

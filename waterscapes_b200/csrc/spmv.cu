@@ -47,7 +47,8 @@ template <int LANES, typename RP>
 __global__ void __launch_bounds__(256)
 k_spmv_vec(int64_t nrows, const RP* __restrict__ rowptr, const int32_t* __restrict__ cols,
            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-           double beta, const uint8_t* __restrict__ rowmask) {
+           double beta, const uint8_t* __restrict__ rowmask, const int* __restrict__ done) {
+    if (done && *done) return;
     const int lane = threadIdx.x & (LANES - 1);
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
     if (row >= nrows) return;   // whole groups exit together (blockDim % LANES == 0)
@@ -138,10 +139,10 @@ void launch_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, d
 
 void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
               const double* vals, const double* x, double* y, double beta, const uint8_t* rowmask,
-              cudaStream_t st) {
+              cudaStream_t st, const int* done) {
     const int threads = 256;
     k_spmv_vec<32, int64_t><<<grid_for(nrows * 32, threads), threads, 0, st>>>(nrows, rowptr, cols, vals, x,
-                                                                                y, beta, rowmask);
+                                                                                y, beta, rowmask, done);
     LAUNCH_CHECK(ctx);
 }
 
