@@ -1,0 +1,143 @@
+"""The reference-facing API (MPETProblem / MPETSolver) on the GPU against the oracle's time loop."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle.mesh import unit_cube_mesh
+from oracle.mpet import MPETOracle, Coef
+
+PI = np.pi
+
+
+def _mms_problem(n, J, theta, dt, T, nonsym=False):
+    from waterscapes_b200.mpet import (MPETProblem, MPETSolver, UnitCubeMesh, Constant, Expression,
+                                       CompiledSubDomain, FacetNormal)
+    S = ((0.0, 2.0), (1.0, 0.0)) if nonsym else ((0.0, 1.0), (1.0, 0.0))
+    params = dict(J=J, E=2.2, nu=0.4545, alpha=(0.5, 0.5), c=(1.0, 1.0), K=(1.0, 1.0), S=S)
+    mesh = UnitCubeMesh(n)
+    time = Constant(0.0)
+    problem = MPETProblem(mesh, time, params=params)
+    u_e = ("0.1*cos(pi*x[0])*sin(pi*x[1])*sin(pi*x[2])*sin(pi*t)",
+           "0.1*sin(pi*x[0])*cos(pi*x[1])*sin(pi*x[2])*sin(pi*t)",
+           "0.1*sin(pi*x[0])*sin(pi*x[1])*cos(pi*x[2])*sin(pi*t)")
+    p_e = ["%d*sin(pi*x[0])*cos(pi*x[1])*sin(pi*x[2])*sin(2*pi*t)" % (i + 1) for i in range(J)]
+    problem.u_bar = Expression(u_e, t=time, degree=2)
+    problem.p_bar = [Expression(p_e[i], t=time, degree=1) for i in range(J)]
+    problem.f = Expression(("sin(pi*x[0])*t", "x[1]*x[2]", "cos(t)*x[0]"), t=time, degree=2)
+    problem.g = [Expression("(1+%d)*x[0]*x[1]*sin(t)" % i, t=time, degree=1) for i in range(J)]
+    n_ = FacetNormal(mesh)
+    problem.s = Expression("0.3*t*x[1]", t=time, degree=2) * n_
+    problem.I = [Expression("0.2*x[2]*(1+t)", t=time, degree=1), Constant(0.1)]
+    problem.beta = [Constant(0.0), Constant(0.7)]
+    problem.p_robin = [Constant(0.0), Expression("0.5*x[0]+t", t=time, degree=1)]
+    on_boundary = CompiledSubDomain("on_boundary")
+    right = CompiledSubDomain("on_boundary && near(x[0], 1.0)")
+    top = CompiledSubDomain("on_boundary && near(x[2], 1.0)")
+    on_boundary.mark(problem.momentum_boundary_markers, 0)
+    right.mark(problem.momentum_boundary_markers, 1)
+    for i in range(J):
+        on_boundary.mark(problem.continuity_boundary_markers[i], 0)
+    right.mark(problem.continuity_boundary_markers[0], 1)
+    top.mark(problem.continuity_boundary_markers[1], 2)
+    solver = MPETSolver(problem, dict(dt=dt, theta=theta, T=T))
+    return mesh, params, problem, solver
+
+
+def _oracle_twin(n, params, theta, dt, T):
+    mesh = unit_cube_mesh(n)
+    o = MPETOracle(mesh, params, dt=dt, theta=theta, T=T)
+    J = params["J"]
+    o.u_bar = Coef(fn=lambda x, t: 0.1 * np.stack([np.cos(PI * x[:, 0]) * np.sin(PI * x[:, 1]) * np.sin(PI * x[:, 2]),
+                                                   np.sin(PI * x[:, 0]) * np.cos(PI * x[:, 1]) * np.sin(PI * x[:, 2]),
+                                                   np.sin(PI * x[:, 0]) * np.sin(PI * x[:, 1]) * np.cos(PI * x[:, 2])],
+                                                  1) * np.sin(PI * t))
+    o.p_bar = [Coef(fn=lambda x, t, i=i: (i + 1) * np.sin(PI * x[:, 0]) * np.cos(PI * x[:, 1]) * np.sin(PI * x[:, 2])
+                    * np.sin(2 * PI * t)) for i in range(J)]
+    o.f = Coef(fn=lambda x, t: np.stack([np.sin(PI * x[:, 0]) * t, x[:, 1] * x[:, 2], np.cos(t) * x[:, 0]], 1), degree=2)
+    o.g = [Coef(fn=lambda x, t, i=i: (1 + i) * x[:, 0] * x[:, 1] * np.sin(t), degree=1) for i in range(J)]
+    o.s = Coef(fn=lambda x, t: 0.3 * t * x[:, 1], degree=2)
+    o.s_times_normal = True
+    o.I = [Coef(fn=lambda x, t: 0.2 * x[:, 2] * (1 + t), degree=1), Coef(value=0.1)]
+    o.beta = [Coef(value=0.0), Coef(value=0.7)]
+    o.p_robin = [Coef(value=0.0), Coef(fn=lambda x, t: 0.5 * x[:, 0] + t, degree=1)]
+    F = o.facets
+    xm = mesh.coords[F["vertices"]]
+    right = np.all(np.abs(xm[:, :, 0] - 1.0) < 3e-16, axis=1)
+    top = np.all(np.abs(xm[:, :, 2] - 1.0) < 3e-16, axis=1)
+    o.momentum_markers[:] = 0
+    o.momentum_markers[right] = 1
+    for i in range(J):
+        o.continuity_markers[i][:] = 0
+    o.continuity_markers[0][right] = 1
+    o.continuity_markers[1][top] = 2
+    return o
+
+
+def _init(solver, o):
+    rng = np.random.default_rng(3)
+    x0 = 0.05 * rng.standard_normal(o.space.N)
+    o.up_ = x0.copy()
+    solver.up_.vector().set_local(x0)
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("theta,nonsym", [(1.0, False), (0.5, False), (0.5, True)])
+def test_solve_matches_oracle_time_loop(theta, nonsym):
+    n, J, dt, T = 4, 2, 0.1, 0.3
+    mesh, params, problem, solver = _mms_problem(n, J, theta, dt, T, nonsym=nonsym)
+    o = _oracle_twin(n, params, theta, dt, T)
+    _init(solver, o)
+    # the pieces first: A (with Robin), b of the first step
+    from waterscapes_b200.mpet import assemble
+    A = solver._assemble_system().to_scipy()
+    Ao = o.on_pattern(o.assemble_lhs())
+    assert _rel(A.data, Ao.data) < 1e-12
+    bo, dofs, vals = o.rhs(0.0)
+    bcs = solver.bcs[0] + solver.bcs[1]
+    solver._sync_dirichlet(bcs)
+    b = solver._rhs(problem.time, 0.0, dt, theta, bcs).get_local()
+    assert _rel(b, bo) < 1e-12, _rel(b, bo)
+    problem.time.assign(0.0)
+    ref = list((up.copy(), t) for up, t in o.solve_direct())
+    k = 0
+    for up, t in solver.solve():
+        xo, to = ref[k]
+        assert abs(t - to) < 1e-12
+        x = up.vector().get_local()
+        sp_ = o.space
+        nu = 3 * sp_.N2
+        errs = [_rel(x[:nu], xo[:nu])] + [_rel(x[sp_.p_dofs(i)], xo[sp_.p_dofs(i)]) for i in range(J)]
+        assert max(errs) < 1e-8, (t, errs)
+        k += 1
+    assert k == len(ref) == 3
+    print("niter", solver.solver_monitor["niter"])
+
+
+def test_step_and_iterative_branch():
+    n, J, dt, T, theta = 3, 2, 0.1, 0.2, 1.0
+    mesh, params, problem, solver = _mms_problem(n, J, theta, dt, T)
+    o = _oracle_twin(n, params, theta, dt, T)
+    _init(solver, o)
+    xo = o.step()
+    solver.step(dt)
+    x = solver.up.vector().get_local()
+    assert _rel(x, xo) < 1e-8
+    assert abs(float(problem.time) - dt) < 1e-14
+    # iterative branch with PETSc-default tolerance: converges, error consistent with rtol
+    mesh, params, problem, solver = _mms_problem(n, J, theta, dt, T)
+    solver.params["direct_solver"] = False
+    o = _oracle_twin(n, params, theta, dt, T)
+    _init(solver, o)
+    ref = [up.copy() for up, t in o.solve_direct()]
+    outs = [up.vector().get_local() for up, t in solver.solve()]
+    assert len(outs) == 2
+    assert _rel(outs[-1], ref[-1]) < 1e-3
+    assert all(nit > 0 for nit in solver.solver_monitor["niter"])
+    u, p0, p1 = solver.up.split(deepcopy=True)
+    assert u.values.shape == (o.space.N2, 3) and p0.values.shape == (o.space.Nv,)
+    assert abs(p0((0.5, 0.5, 0.5)) - float(p0.values[np.argmin(np.linalg.norm(mesh.coordinates - 0.5, axis=1))])) < 0.5
