@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the MPET timestep hot path (assemble + Krylov solve) on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...          # CPU restatement of the reference path
+
+One "step" = the body of the reference's MPETSolver.step (src/mpet/mpet/mpetsolver.py:317-379):
+assemble A (+ Robin), Dirichlet conditions, assemble b (L, L1[i], L0), solve to the reference
+tolerance.  Metric: whole-job DOF/s (unknowns of the block system advanced one timestep per second).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mpet_timestep_dof_per_s"
+UNIT = "DOF/s"
+DEFAULT_CONFIG = "cfg5"          # A=3, n=72 per GPU: ~10.3 M dofs per GPU (BASELINE.json configs[4])
+CPU_SAMPLE_N = 10                # bounded CPU sample of the same workload family
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--n", type=int, default=None, help="override the mesh resolution of the config")
+    ap.add_argument("--rtol", type=float, default=1e-6,
+                    help="Krylov tolerance (reference authors' intent: sandbox/2D_1net_totalpressure.py:168-170)")
+    ap.add_argument("--maxit", type=int, default=10000)
+    ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu = gpu_index
+        self.path = "/tmp/bench_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per SpMV launch from the committed ncu --set full capture, if present."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))
+        return d
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def build_oracle_problem(config, n):
+    """The workload of waterscapes_b200/workloads.py restated on the oracle's classes (no product code)."""
+    import numpy as np
+    from oracle.mesh import unit_cube_mesh, SimplexMesh
+    from oracle.mpet import MPETOracle, Coef
+    mm = 133.32
+    if config == "cfg2":
+        mesh = unit_cube_mesh(n)
+        params = dict(J=1, E=500.0, nu=0.49, alpha=(1.0,), c=(1.0e-2,), K=(1.0e-5,), S=((0.0,),))
+        o = MPETOracle(mesh, params, dt=0.05, theta=1.0)
+        xm = mesh.coords[o.facets["vertices"]]
+        o.momentum_markers[:] = 1
+        o.momentum_markers[np.all(np.abs(xm[:, :, 2]) < 3e-16, axis=1)] = 0
+        o.s = Coef(value=lambda t: 133.322 * 0.15 * np.sin(2 * np.pi * t))
+        o.s_times_normal = True
+        o.continuity_markers[0][:] = 1
+        o.continuity_markers[0][np.all(np.abs(xm[:, :, 2] - 1.0) < 3e-16, axis=1)] = 0
+        return o
+    if config == "cfg1":
+        mesh = unit_cube_mesh(n)
+        mu, lm = 1.0, 10.0
+        E, nu = mu * (3 * lm + 2 * mu) / (lm + mu), lm / (2 * (lm + mu))
+        params = dict(J=2, E=E, nu=nu, alpha=(0.5, 0.5), c=(1.0, 1.0), K=(1.0, 1.0), S=((0.0, 1.0), (1.0, 0.0)))
+        o = MPETOracle(mesh, params, dt=0.1, theta=1.0)
+        pi = np.pi
+        o.u_bar = Coef(fn=lambda x, t: 0.1 * np.stack(
+            [np.cos(pi * x[:, 0]) * np.sin(pi * x[:, 1]) * np.sin(pi * x[:, 2]),
+             np.sin(pi * x[:, 0]) * np.cos(pi * x[:, 1]) * np.sin(pi * x[:, 2]),
+             np.sin(pi * x[:, 0]) * np.sin(pi * x[:, 1]) * np.cos(pi * x[:, 2])], 1) * np.sin(pi * t))
+        o.p_bar = [Coef(fn=lambda x, t, i=i: (i + 1) * np.sin(pi * x[:, 0]) * np.cos(pi * x[:, 1])
+                        * np.sin(pi * x[:, 2]) * np.sin(2 * pi * t)) for i in range(2)]
+        o.f = Coef(fn=lambda x, t: np.stack([np.sin(pi * x[:, 0]) * np.sin(pi * t), np.cos(pi * x[:, 1]) * np.sin(pi * t),
+                                             x[:, 2] * np.sin(pi * t)], 1), degree=2)
+        o.g = [Coef(fn=lambda x, t, i=i: (i + 1) * np.cos(pi * x[:, 0]) * np.cos(2 * pi * t), degree=1) for i in range(2)]
+        o.momentum_markers[:] = 0
+        for i in range(2):
+            o.continuity_markers[i][:] = 0
+        x2 = o.space.node2_coords()
+        u0 = o.u_bar.at_points(x2, 0.0)
+        for k in range(3):
+            o.up_[o.space.u_dofs(k)] = u0[:, k]
+        return o
+    J = {"cfg3": 4, "cfg4": 4, "cfg5": 3}[config]
+    base = unit_cube_mesh(n)
+    mesh = SimplexMesh(base.coords * 120.0, base.cells)
+    c = (3.9e-4, 2.9e-4, 1.5e-5, 2.9e-4)
+    alpha = (0.49, 0.25, 0.01, 0.25)
+    kappa = (1.4e-14, 1.e-10, 1.e-10, 1.e-10)
+    eta = (8.9e-4, 2.67e-3, 2.67e-3, 2.67e-3)
+    K = [kappa[i] / eta[i] * 1.e6 for i in range(4)]
+    s = 1.0e-6
+    S = ((0.0, 0.0, s, s), (0.0, 0.0, 0.0, s), (s, 0.0, 0.0, s), (s, s, s, 0.0))
+    params = dict(J=J, alpha=alpha[:J], K=K[:J], S=tuple(r[:J] for r in S[:J]), c=c[:J], nu=0.4999, E=1500)
+    o = MPETOracle(mesh, params, dt=0.0125, theta=0.5)
+    pbar = [Coef(value=lambda t: mm * (3.0 + 2 * np.sin(2 * np.pi * t))),
+            Coef(value=lambda t: mm * (70.0 + 10.0 * np.sin(2.0 * np.pi * t))),
+            Coef(value=mm * 6.0), Coef(value=mm * (6.0 + 70) / 2)]
+    o.p_bar = pbar[:J]
+    o.momentum_markers[:] = 0
+    for i in range(J):
+        o.continuity_markers[i][:] = 1 if i == 3 else 0
+        o.up_[o.space.p_dofs(i)] = float(pbar[i].const(0.0))
+    return o
+
+
+def run_cpu(config, n, rtol, steps, warmup, maxit):
+    """(seconds per step, dofs, iterations) of the oracle's step on the host."""
+    import numpy as np
+    from oracle.krylov import minres, BlockAMG
+    o = build_oracle_problem(config, n)
+    dofs, _ = o.dirichlet(o.t)
+    M = BlockAMG(o, dofs)                       # hierarchy set-up is outside the step on both arms
+    B = o.assemble_prev_operator()
+    mask = np.zeros(o.space.N, dtype=bool)
+    mask[dofs] = True
+    x = o.up_.copy()
+    times, iters = [], []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        A = o.assemble_lhs()                    # re-assembled every step like MPETSolver.step
+        b, _, vals = o.rhs(o.t, B)
+        x0 = x.copy()
+        x0[dofs] = vals
+        x, info = minres(A, b, x0, M, mask=mask, rtol=rtol, maxit=maxit)
+        t1 = time.perf_counter()
+        o.t += o.dt
+        o.up_ = x.copy()
+        if k >= warmup:
+            times.append(t1 - t0)
+            iters.append(info["niter"])
+    return sum(times) / len(times), o.space.N, iters
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        sec, dofs, iters = run_cpu(args.config, args.cpu_n, args.rtol, max(1, args.steps), max(0, min(args.warmup, 1)),
+                                   args.maxit)
+        val = dofs / sec
+        sample = "%s family at n=%d (%d dofs), %d step(s), MINRES its %s" % (args.config, args.cpu_n, dofs,
+                                                                             len(iters), iters)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: %s" % (args.config, sample), "rtol": args.rtol,
+                           "note": "CPU restatement (numpy/scipy oracle) of the reference path; DOLFIN/PETSc "
+                                   "are not installable offline"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                                 "host_threads_available": threads},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from waterscapes_b200.workloads import make_problem, CONFIGS
+    from waterscapes_b200.mpet import MPETSolver
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = CONFIGS[args.config]
+    n = args.n or cfg["n"]
+    problem, sp, init = make_problem(args.config, n)
+    sp = dict(sp, direct_solver=False, krylov_rtol=args.rtol, krylov_maxit=args.maxit)
+    solver = MPETSolver(problem, sp, device=local_rank)
+    eng = solver.engine
+    S = eng.sizes
+    init(solver)
+    dt = sp["dt"]
+
+    def one_step():
+        solver.step(dt)
+        solver.up_.assign(solver.up)
+
+    # set-up outside the timed region on both arms: AMG hierarchy (first solve builds it)
+    t_setup0 = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    setup_s = time.perf_counter() - t_setup0
+
+    # ---- device-resident timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.profile(enable=1)
+    eng.launch_count(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = []
+    for _ in range(args.steps):
+        one_step()
+        iters.append(solver.solver_monitor["niter"][-1])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count()
+    prof = eng.profile(enable=0)
+    clocks = sampler.stop()
+
+    # ---- end-to-end: host buffers in, host buffers out, through the public API
+    N = S["N"]
+    h_in = torch.empty(N, dtype=torch.float64).pin_memory()
+    h_out = torch.empty(N, dtype=torch.float64).pin_memory()
+    h_in.copy_(solver.up_.x)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        solver.up_.x.copy_(h_in, non_blocking=True)          # H2D: previous state
+        solver.step(dt)
+        h_out.copy_(solver.up.x, non_blocking=True)           # D2H: new state
+        torch.cuda.current_stream().synchronize()
+        h_in.copy_(h_out)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    total_dofs = N * world
+    ms_step = ms / args.steps
+    value = total_dofs / (ms_step / 1e3)
+    e2e_value = total_dofs / (ms_e2e / args.steps / 1e3)
+
+    peak, peak_src = measured_peak()
+    spmv_bytes = 12 * S["nnz"] + 20 * S["N"]
+    spmv_ms = prof["spmv"]["ms"] / max(1, prof["spmv"]["count"])
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_spmv_vec<32> (block-system CSR SpMV inside MINRES)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                "avg_launch_ms": spmv_ms, "launches_timed": prof["spmv"]["count"],
+                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "share_of_step": {"spmv": prof["spmv"]["ms"] / ms, "preconditioner": prof["pc"]["ms"] / ms,
+                                  "assemble_lhs": prof["assemble"]["ms"] / ms, "rhs_prev": prof["rhs"]["ms"] / ms}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: [P2]^3x[P1]^%d MPET on BoxMesh(%d^3) per GPU, %d cells, %d dofs, %d nnz; "
+                                   "step = assemble A + b, Dirichlet, MINRES+block-AMG to rtol %g"
+                                   % (args.config, S["A"], n, S["Nc"], N, S["nnz"], args.rtol),
+                       "dofs_per_gpu": N, "nnz_per_gpu": S["nnz"], "rtol": args.rtol, "krylov_iterations": iters,
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                       "l2": "inputs (%.1f GB matrix) larger than the 126 MB L2" % (12 * S["nnz"] / 1e9),
+                       "amg_setup_s_excluded": round(setup_s, 2)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N},
+            "gpu_launches": launches,
+            "roofline": roofline}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, dofs, cit = run_cpu(args.config, args.cpu_n, args.rtol, 1, 0, args.maxit)
+        line["cpu_baseline"] = {"value": dofs / sec, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%s family at n=%d (%d dofs), 1 step, %s MINRES iterations, %.1f s"
+                                          % (args.config, args.cpu_n, dofs, cit, sec)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -136,6 +136,11 @@ int mpet_set_partition(mpet_ctx* ctx, const int32_t* owner_of_local_dof_dev, int
 /* ---- instrumentation ---------------------------------------------------------------------------
  * number of kernels this library launched since the last reset (bench.py's "gpu_launches") */
 int64_t mpet_launch_count(mpet_ctx* ctx, int reset);
+/* CUDA-event profile of the library's own launches (bench.py's live roofline measurement).
+ * enable: 1/0 = reset counters and switch on/off, -1 = leave unchanged.  out_host (nullable) f64[16]:
+ * [0..7] device ms per category (0 SpMV of A, 1 preconditioner, 3 assemble_lhs, 4 rhs_prev),
+ * [8..15] launch-group counts.  Synchronises the device. */
+int mpet_profile(mpet_ctx* ctx, int enable, double* out_host);
 int64_t mpet_device_bytes(mpet_ctx* ctx);
 
 #ifdef __cplusplus

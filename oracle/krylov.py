@@ -1,0 +1,329 @@
+"""Oracle restatement of the Krylov path (test infrastructure; see oracle/__init__.py).
+
+What the reference asks PETSc/hypre to do -- ``PETScKrylovSolver("minres", "hypre_amg")`` with
+``set_operators(Acopy, P)`` (mpetsolver.py:507,553-556; mpettotalpressuresolver.py:448,492-493) --
+restated with scipy.sparse matvecs:
+
+* ``minres``: PETSc's KSPMINRES recurrence [EXT: petsc/src/ksp/ksp/impls/minres/minres.c], one operator
+  and one preconditioner application per iteration, convergence test on the preconditioned norm
+  ``|eta| <= max(rtol * |eta_0|, atol)``, Dirichlet rows handled as in ``apply_symmetric``
+  (bc_symmetric.py:11-22).
+* ``BlockAMG``: the block-diagonal V-cycle of DESIGN.md section "Preconditioner" (hypre BoomerAMG itself is
+  an un-vendored dependency; its defaults are not reproducible here).  This class restates, loop for
+  loop, the hierarchy the CUDA library builds (p-coarsening P2 -> P1, greedy smoothed aggregation,
+  degree-2 Chebyshev smoothing, dense coarsest solve) so that iteration counts can be compared.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+CHEB_DEGREE = 2
+CHEB_RATIO = 4.0
+COARSE_MAX = 300
+DENSE_MAX = 700
+MAX_LEVELS = 12
+
+
+# ------------------------------------------------------------------------------------------ MINRES
+def minres(A, b, x0, M, mask=None, rtol=1e-5, atol=1e-50, maxit=10000):
+    """Preconditioned MINRES.  ``A``: scipy matrix WITHOUT boundary conditions; ``mask``: bool array of
+    Dirichlet rows (x0 must carry the boundary values there); ``M(r)``: SPD preconditioner.
+    Returns (x, info dict)."""
+    x = x0.copy()
+    free = np.ones(b.shape[0], dtype=bool) if mask is None else ~mask
+
+    def op(v):
+        y = A @ v
+        if mask is not None:
+            y[mask] = v[mask]
+        return y
+
+    r = np.where(free, b - A @ x, 0.0)
+    z = M(r)
+    dp = r @ z
+    if dp < 0:
+        raise RuntimeError("indefinite preconditioner")
+    beta = np.sqrt(dp)
+    norm0 = beta
+    tol = max(rtol * beta, atol)
+    info = dict(niter=0, converged=False, res0=norm0, rel_res=1.0)
+    if beta <= tol or beta == 0.0:
+        info.update(converged=True, rel_res=0.0 if beta == 0 else 1.0)
+        return x, info
+    eta = beta
+    c = c_old = 1.0
+    s = s_old = 0.0
+    v, u = r / beta, z / beta
+    v_old = np.zeros_like(v)
+    u_old = np.zeros_like(v)
+    w1 = np.zeros_like(v)
+    w2 = np.zeros_like(v)
+    for it in range(1, maxit + 1):
+        r = op(u)
+        alpha = r @ u
+        z = M(r)
+        r = r - alpha * v - beta * v_old
+        z = z - alpha * u - beta * u_old
+        beta_old = beta
+        dp = max(r @ z, 0.0)
+        beta = np.sqrt(dp)
+        c_oold, s_oold = c_old, s_old
+        c_old, s_old = c, s
+        rho0 = c_old * alpha - c_oold * s_old * beta_old
+        rho1 = np.sqrt(rho0 * rho0 + beta * beta)
+        rho2 = s_old * alpha + c_oold * c_old * beta_old
+        rho3 = s_oold * beta_old
+        c, s = rho0 / rho1, beta / rho1
+        wn = (u - rho2 * w1 - rho3 * w2) / rho1
+        w2, w1 = w1, wn
+        x = x + c * eta * wn
+        eta = -s * eta
+        v_old, u_old = v, u
+        if beta != 0.0:
+            v, u = r / beta, z / beta
+        info["niter"] = it
+        info["rel_res"] = abs(eta) / norm0
+        if abs(eta) <= tol:
+            info["converged"] = True
+            break
+        if beta == 0.0:
+            break
+    return x, info
+
+
+# ------------------------------------------------------------------------------------------ AMG
+def _sa_prolongator(A, theta):
+    """Greedy aggregation + one damped-Jacobi smoothing step (same passes, same order as amg.cu)."""
+    A = A.tocsr()
+    n = A.shape[0]
+    rp, ci, av = A.indptr, A.indices, A.data
+    diag = A.diagonal().copy()
+    diag[diag == 0] = 1.0
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    off = (ci != rows) & (av != 0.0)
+    scale = np.sqrt(np.abs(diag[rows] * diag[ci]))
+    strong = off & (np.abs(av) >= theta * scale)
+    isolated = np.bincount(rows[off], minlength=n) == 0
+    S = sp.csr_matrix((np.where(strong, np.abs(av) / scale, 0.0)[strong], ci[strong],
+                       np.concatenate([[0], np.cumsum(np.bincount(rows[strong], minlength=n))])), shape=(n, n))
+    srp, sci, sval = S.indptr, S.indices, S.data
+    agg = np.full(n, -1, dtype=np.int64)
+    nagg = 0
+    for r in range(n):                                    # pass 1
+        if agg[r] != -1 or isolated[r] or srp[r + 1] == srp[r]:
+            continue
+        nb = sci[srp[r]:srp[r + 1]]
+        if np.any(agg[nb] != -1):
+            continue
+        agg[r] = nagg
+        agg[nb] = nagg
+        nagg += 1
+    agg2 = agg.copy()
+    for r in range(n):                                    # pass 2
+        if agg[r] != -1 or isolated[r]:
+            continue
+        nb = sci[srp[r]:srp[r + 1]]
+        ok = agg[nb] != -1
+        if ok.any():
+            w = np.where(ok, sval[srp[r]:srp[r + 1]], -1.0)
+            agg2[r] = agg[nb[np.argmax(w)]]
+    agg = agg2
+    for r in range(n):                                    # pass 3
+        if agg[r] != -1 or isolated[r]:
+            continue
+        agg[r] = nagg
+        nb = sci[srp[r]:srp[r + 1]]
+        take = nb[(agg[nb] == -1) & ~isolated[nb]]
+        agg[take] = nagg
+        nagg += 1
+    if nagg == 0:
+        return None
+    have = agg >= 0
+    T = sp.csr_matrix((np.ones(have.sum()), (np.nonzero(have)[0], agg[have])), shape=(n, nagg))
+    x = 1.0 + 0.37 * np.sin(1.7 * np.arange(n))
+    rho = 1.0
+    for _ in range(15):
+        x = x / np.linalg.norm(x)
+        y = (A @ x) / diag
+        rho = np.linalg.norm(y)
+        x = y
+    rho *= 1.1
+    omega = (4.0 / 3.0) / rho
+    Dinv = sp.diags(np.where(isolated, 0.0, 1.0 / diag))
+    keep = sp.diags(np.where(isolated, 0.0, 1.0))
+    P = keep @ T - omega * (Dinv @ (A @ T))
+    return P.tocsr()
+
+
+class _Level:
+    pass
+
+
+class ScalarAMG:
+    """V-cycle hierarchy for one scalar SPD block (identity rows on eliminated Dirichlet dofs)."""
+
+    def __init__(self, A0, first_coarse=None):
+        self.levels = []
+        self._push(A0.tocsr(), None)
+        if first_coarse is not None:
+            P, A1 = first_coarse
+            self._push(A1.tocsr(), P.tocsr())
+        A = self.levels[-1].A
+        theta = 0.08
+        while A.shape[0] > COARSE_MAX and len(self.levels) < MAX_LEVELS:
+            P = _sa_prolongator(A, theta)
+            if P is None or P.shape[1] > 0.8 * A.shape[0]:
+                break
+            Ac = (P.T @ (A @ P)).tocsr()
+            Ac.sort_indices()
+            self._push(Ac, P)
+            A = Ac
+            theta *= 0.5
+        self.coarse_inv = None
+        if A.shape[0] <= DENSE_MAX:
+            self.coarse_inv = np.linalg.inv(A.toarray())
+
+    def _push(self, A, P):
+        L = _Level()
+        L.A, L.P = A, P
+        d = A.diagonal().copy()
+        d[d == 0] = 1.0
+        L.dinv = 1.0 / d
+        n = A.shape[0]
+        gersh = float(np.max(np.asarray(abs(A).sum(axis=1)).ravel() * np.abs(L.dinv)))
+        i = np.arange(n)
+        x = 1.0 + 0.5 * np.sin(0.37 * i + 0.1 * (i % 7))
+        lam = 0.0
+        for _ in range(20):
+            y = (A @ x) * L.dinv
+            lam = np.linalg.norm(y)
+            if lam == 0:
+                break
+            x = y / lam
+        est = 1.1 * lam
+        L.lmax = gersh if (est <= 0 or est > gersh) else est
+        self.levels.append(L)
+
+    def _cheb(self, L, b, x):
+        lmax, lmin = L.lmax, L.lmax / CHEB_RATIO
+        theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+        sigma = theta / delta
+        rho_old = 1.0 / sigma
+        d = None
+        for k in range(CHEB_DEGREE):
+            if k == 0:
+                r = b if x is None else b - L.A @ x
+                d = (1.0 / theta) * (L.dinv[:, None] * r)
+                x = d.copy() if x is None else x + d
+            else:
+                rho = 1.0 / (2.0 * sigma - rho_old)
+                r = b - L.A @ x
+                d = rho * rho_old * d + (2.0 * rho / delta) * (L.dinv[:, None] * r)
+                x = x + d
+                rho_old = rho
+        return x
+
+    def _vcycle(self, lev, b):
+        L = self.levels[lev]
+        if lev == len(self.levels) - 1:
+            if self.coarse_inv is not None:
+                return self.coarse_inv @ b
+            return self._cheb(L, b, None)
+        x = self._cheb(L, b, None)
+        r = b - L.A @ x
+        C = self.levels[lev + 1]
+        xc = self._vcycle(lev + 1, C.P.T @ r)
+        x = x + C.P @ xc
+        return self._cheb(L, b, x)
+
+    def apply(self, B):
+        """B: [n, nrhs] -> approximate A^-1 B."""
+        B = B.reshape(B.shape[0], -1)
+        return self._vcycle(0, B)
+
+
+def _eliminate(M, mask):
+    """Symmetric Dirichlet elimination with unit diagonal (apply_symmetric(bc, P), mpetsolver.py:503-504)."""
+    M = M.tocsr(copy=True)
+    rows = np.repeat(np.arange(M.shape[0]), np.diff(M.indptr))
+    kill = mask[rows] | mask[M.indices]
+    M.data[kill] = 0.0
+    M = M + sp.diags(mask.astype(float))
+    M = M.tocsr()
+    M.sort_indices()
+    return M
+
+
+class BlockAMG:
+    """Block-diagonal preconditioner: shared scalar P2 block mu*(grad,grad) for the three displacement
+    components (p-coarsened to P1, then aggregation) + one P1 block per network."""
+
+    def __init__(self, oracle, dirichlet_dofs):
+        o = oracle
+        sp_ = o.space
+        assert o.d == 3 and sp_.nreal == 0 and sp_.perm is None
+        from .mpet import convert_to_mu_lmbda
+        mu, _ = convert_to_mu_lmbda(o.E, o.nu)
+        N2, Nv, A = sp_.N2, sp_.Nv, o.A
+        mask = np.zeros(sp_.N, dtype=bool)
+        mask[dirichlet_dofs] = True
+        for k in (1, 2):
+            assert np.array_equal(mask[:N2], mask[k * N2:(k + 1) * N2])
+        P = o.assemble_prec().tocsr()
+        m2 = mask[:N2]
+        A2 = _eliminate(P[:N2, :N2], m2)
+        # P1 stiffness * mu on the vertex block, eliminated with the vertex part of the mask
+        ones = MPETOracleScalar(o)
+        A1 = _eliminate(mu * ones.p1_stiffness(), m2[:Nv])
+        ev = sp_.edge_vertices
+        rows, cols, vals = [], [], []
+        for r in range(N2):
+            if m2[r]:
+                continue
+            if r < Nv:
+                rows.append(r); cols.append(r); vals.append(1.0)
+            else:
+                for v in ev[r - Nv]:
+                    if not m2[v]:
+                        rows.append(r); cols.append(v); vals.append(0.5)
+        P21 = sp.csr_matrix((vals, (rows, cols)), shape=(N2, Nv))
+        self.u = ScalarAMG(A2, first_coarse=(P21, A1))
+        self.p = []
+        for i in range(A):
+            d = sp_.p_dofs(i)
+            self.p.append(ScalarAMG(_eliminate(P[d][:, d], mask[d])))
+        self.N2, self.Nv, self.A = N2, Nv, A
+
+    def __call__(self, r):
+        N2, Nv = self.N2, self.Nv
+        z = np.empty_like(r)
+        U = self.u.apply(r[:3 * N2].reshape(3, N2).T)
+        z[:3 * N2] = U.T.reshape(-1)
+        for i in range(self.A):
+            lo = 3 * N2 + i * Nv
+            z[lo:lo + Nv] = self.p[i].apply(r[lo:lo + Nv])[:, 0]
+        return z
+
+    def num_levels(self):
+        return [len(self.u.levels)] + [len(h.levels) for h in self.p]
+
+
+class MPETOracleScalar:
+    """Scalar P1 operators on the oracle's mesh (helper for the p-coarsened level)."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def p1_stiffness(self):
+        o = self.o
+        Nv = o.space.Nv
+        nc = o.mesh.num_cells
+        rows, cols, vals = [], [], []
+        for c0 in range(0, nc, 8192):
+            cells = np.arange(c0, min(nc, c0 + 8192))
+            _, _, _, Lp = o.element_blocks(cells)
+            cv = o.mesh.cells[cells]
+            rows.append(np.repeat(cv[:, :, None], 4, axis=2).ravel())
+            cols.append(np.repeat(cv[:, None, :], 4, axis=1).ravel())
+            vals.append(Lp.ravel())
+        M = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(Nv, Nv))
+        return M.tocsr()

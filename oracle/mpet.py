@@ -634,3 +634,33 @@ class MPETOracle:
                 gpe = grad_p[i](xq.reshape(-1, d), t).reshape(gph.shape)
                 out["p_H1"].append(np.sqrt(l2 ** 2 + np.einsum("cq,cqm,cqm->", w, gph - gpe, gph - gpe)))
         return out
+
+
+# ---------------------------------------------------------------------------------- iterative twin
+def _solve_iterative(self, rtol=1e-5, atol=1e-50, maxit=10000, monitor=None, reassemble=False):
+    """Generator twin of ``MPETSolver.solve_iterative`` (mpetsolver.py:465-569): MINRES preconditioned
+    by the block-diagonal AMG V-cycle (oracle/krylov.py).  ``reassemble=True`` re-assembles A every
+    step like ``MPETSolver.step`` (mpetsolver.py:335)."""
+    from .krylov import minres, BlockAMG
+    A = self.assemble_lhs()
+    B = self.assemble_prev_operator()
+    dofs, _ = self.dirichlet(self.t)
+    M = BlockAMG(self, dofs)
+    mask = np.zeros(self.space.N, dtype=bool)
+    mask[dofs] = True
+    self.up = self.up_.copy()
+    while self.t < self.T - 1e-9:
+        if reassemble:
+            A = self.assemble_lhs()
+        b, _, vals = self.rhs(self.t, B)
+        x0 = self.up.copy()
+        x0[dofs] = vals
+        self.t = self.t + self.dt
+        self.up, info = minres(A, b, x0, M, mask=mask, rtol=rtol, atol=atol, maxit=maxit)
+        if monitor is not None:
+            monitor.append(info)
+        yield self.up, self.t
+        self.up_ = self.up.copy()
+
+
+MPETOracle.solve_iterative = _solve_iterative

@@ -1,0 +1,60 @@
+"""CPU: host-side logic of the reference-facing API (no kernels): meshes, markers, expressions,
+boundary dof sets, facet operators -- checked against the oracle's independent implementation."""
+import numpy as np
+import pytest
+
+from oracle.mesh import unit_cube_mesh
+from oracle.mpet import MPETOracle, Coef
+from waterscapes_b200.mpet.dolfin_shim import (UnitCubeMesh, BoxMesh, Constant, Expression, CompiledSubDomain,
+                                               MeshFunction, FacetNormal, NormalProduct, Parameters)
+from waterscapes_b200.mpet.mpetproblem import MPETProblem, convert_to_E_nu, convert_to_mu_lmbda
+from waterscapes_b200.workloads import sizes
+
+
+def test_box_mesh_matches_oracle_generator():
+    for n in (1, 2, 5):
+        m = UnitCubeMesh(n)
+        o = unit_cube_mesh(n)
+        assert np.array_equal(m.cells, o.cells)
+        assert np.allclose(m.coordinates, o.coords, atol=0)
+    F = UnitCubeMesh(3).exterior_facets()
+    Fo = unit_cube_mesh(3).exterior_facets()
+    for k in ("vertices", "cell", "local"):
+        assert np.array_equal(F[k], Fo[k])
+    assert F["cell"].shape[0] == 6 * 2 * 9
+
+
+def test_expression_strings_and_time_constant():
+    t = Constant(0.25)
+    e = Expression("mmHg2Pa*(3.0 + 2*sin(2*pi*t)) + x[0]*x[1]", mmHg2Pa=133.32, t=t, degree=1)
+    x = np.array([[0.5, 2.0, 0.0], [1.0, 1.0, 1.0]])
+    assert np.allclose(e.eval_points(x), 133.32 * (3 + 2 * np.sin(np.pi / 2)) + x[:, 0] * x[:, 1])
+    t.assign(0.5)
+    assert np.allclose(e.eval_points(x), 133.32 * 3 + x[:, 0] * x[:, 1])
+    v = Expression(("x[0]", "pow(x[1], 2)", "t"), t=t, degree=2)
+    assert v.value_shape() == (3,) and v.eval_points(x).shape == (2, 3)
+    assert isinstance(e * FacetNormal(None), NormalProduct)
+
+
+def test_subdomain_marking_and_problem_defaults():
+    mesh = UnitCubeMesh(3)
+    problem = MPETProblem(mesh, Constant(0.0), params=dict(J=2, E=1.0, nu=0.3, alpha=(1, 1), K=(1, 1),
+                                                           S=((0, 0), (0, 0)), c=(1, 1)))
+    import sys
+    assert np.all(problem.momentum_boundary_markers.array() == sys.maxsize)
+    CompiledSubDomain("on_boundary").mark(problem.momentum_boundary_markers, 0)
+    CompiledSubDomain("on_boundary && near(x[0], 1.0)").mark(problem.momentum_boundary_markers, 1)
+    arr = problem.momentum_boundary_markers.array()
+    assert (arr == 1).sum() == 2 * 9 and (arr == 0).sum() == 5 * 2 * 9
+    CompiledSubDomain("on_boundary && x[2] > 0.5 && x[1] < 0.5").mark(problem.continuity_boundary_markers[1], 2)
+    assert (problem.continuity_boundary_markers[1].array() == 2).sum() > 0
+    assert len(problem.g) == 2 and float(problem.g[0]) == 0.0
+    E, nu = convert_to_E_nu(1.0, 10.0)
+    mu, lm = convert_to_mu_lmbda(E, nu)
+    assert abs(mu - 1.0) < 1e-14 and abs(lm - 10.0) < 1e-13
+
+
+def test_sizes_formula():
+    s = sizes(71, 4)
+    assert s["dofs"] == 10265613 and s["nnz"] == 1400017525 and s["cells"] == 2147466
+    p = Parameters("x"); p.add("dt", 0.1); p.update(dict(dt=0.2)); assert p["dt"] == 0.2

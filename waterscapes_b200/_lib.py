@@ -47,6 +47,7 @@ PROTOTYPES = {
     "mpet_attach_comm": (_int, [_c_ctx, _p, _int, _int]),
     "mpet_set_partition": (_int, [_c_ctx, _p, _i64, _p]),
     "mpet_launch_count": (_i64, [_c_ctx, _int]),
+    "mpet_profile": (_int, [_c_ctx, _int, C.POINTER(_f64)]),
     "mpet_device_bytes": (_i64, [_c_ctx]),
 }
 

@@ -37,7 +37,59 @@ __global__ void k_cell_dofs(const int32_t* __restrict__ cell_nodes, int64_t nc, 
 }
 }  // namespace
 
+static cudaEvent_t prof_event(mpet_ctx* ctx) {
+    if (!ctx->prof.pool.empty()) {
+        cudaEvent_t e = ctx->prof.pool.back();
+        ctx->prof.pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+}
+
+cudaEvent_t prof_begin(mpet_ctx* ctx, cudaStream_t st) {
+    if (!ctx->prof.on || ctx->prof.pending.size() > 20000) return nullptr;
+    cudaEvent_t a = prof_event(ctx);
+    CUDA_CHECK(cudaEventRecord(a, st));
+    return a;
+}
+
+void prof_end(mpet_ctx* ctx, int cat, cudaEvent_t a, cudaStream_t st) {
+    if (!a) return;
+    cudaEvent_t b = prof_event(ctx);
+    CUDA_CHECK(cudaEventRecord(b, st));
+    ctx->prof.pending.push_back({cat, a, b});
+}
+
+void prof_collect(mpet_ctx* ctx) {   // call after the stream has been synchronised
+    for (auto& sp : ctx->prof.pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            ctx->prof.ms[sp.cat] += ms;
+            ctx->prof.cnt[sp.cat] += 1;
+        }
+        ctx->prof.pool.push_back(sp.a);
+        ctx->prof.pool.push_back(sp.b);
+    }
+    ctx->prof.pending.clear();
+}
+
 extern "C" {
+
+int mpet_profile(mpet_ctx* ctx, int enable, double* out_host) {
+    MPET_TRY(ctx)
+    CUDA_CHECK(cudaDeviceSynchronize());
+    prof_collect(ctx);
+    if (out_host) {
+        for (int i = 0; i < PROF_NCAT; ++i) { out_host[i] = ctx->prof.ms[i]; out_host[PROF_NCAT + i] = (double)ctx->prof.cnt[i]; }
+    }
+    if (enable >= 0) {
+        ctx->prof.on = enable != 0;
+        for (int i = 0; i < PROF_NCAT; ++i) { ctx->prof.ms[i] = 0; ctx->prof.cnt[i] = 0; }
+    }
+    MPET_CATCH(ctx)
+}
 
 int mpet_abi_version(void) { return 1; }
 
@@ -149,7 +201,9 @@ int mpet_set_params(mpet_ctx* ctx, double E, double nu, const double* alpha, con
 
 int mpet_assemble_lhs(mpet_ctx* ctx, void* stream) {
     MPET_TRY(ctx)
+    cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
     assemble_lhs(ctx, as_stream(stream));
+    prof_end(ctx, PROF_ASM, pe, as_stream(stream));
     MPET_CATCH(ctx)
 }
 
@@ -190,7 +244,9 @@ int mpet_set_dirichlet_values(mpet_ctx* ctx, const double* vals, void* stream) {
 
 int mpet_rhs_prev(mpet_ctx* ctx, const double* up_prev, double* b, void* stream) {
     MPET_TRY(ctx)
+    cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
     rhs_prev(ctx, up_prev, b, as_stream(stream));
+    prof_end(ctx, PROF_RHS, pe, as_stream(stream));
     MPET_CATCH(ctx)
 }
 

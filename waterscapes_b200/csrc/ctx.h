@@ -73,8 +73,20 @@ struct AmgHierarchy {
     int64_t coarse_n = 0;
 };
 
+// CUDA-event profiler: per-category device time of the launches made inside the library
+enum { PROF_SPMV = 0, PROF_PC = 1, PROF_VEC = 2, PROF_ASM = 3, PROF_RHS = 4, PROF_NCAT = 8 };
+struct Prof {
+    bool on = false;
+    struct Span { int cat; cudaEvent_t a, b; };
+    std::vector<Span> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[PROF_NCAT] = {0};
+    int64_t cnt[PROF_NCAT] = {0};
+};
+
 struct mpet_ctx {
     int device = 0;
+    Prof prof;
     std::string err;
     int64_t launches = 0;
     int64_t bytes = 0;
@@ -160,6 +172,11 @@ inline int grid_for(int64_t work, int block) {
         (ctx)->launches++;            \
         CUDA_CHECK(cudaGetLastError()); \
     } while (0)
+
+// profiler (api.cu)
+cudaEvent_t prof_begin(mpet_ctx* ctx, cudaStream_t st);
+void prof_end(mpet_ctx* ctx, int cat, cudaEvent_t a, cudaStream_t st);
+void prof_collect(mpet_ctx* ctx);
 
 // graph.cu
 void build_space(mpet_ctx* ctx, cudaStream_t st);

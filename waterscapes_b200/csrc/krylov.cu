@@ -362,11 +362,15 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     int enq = 0;
     while (true) {
         for (int q = 0; q < check_every && enq < ctx->maxit; ++q, ++enq) {
+            cudaEvent_t pe = prof_begin(ctx, st);
             csr_spmv(ctx, n, ctx->rowptr, ctx->cols, ctx->vals, k->u, k->r, 0.0, mask, st, done);
+            prof_end(ctx, PROF_SPMV, pe, st);
             dot_to(ctx, k, k->r, k->u, done, st);
             k_minres_alpha<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
             LAUNCH_CHECK(ctx);
+            pe = prof_begin(ctx, st);
             pc_apply_flag(ctx, k->r, k->z, done, st);
+            prof_end(ctx, PROF_PC, pe, st);
             k_minres_update<<<kRedBlocks, kRedThreads, 0, st>>>(n, k->sc, k->v, k->v_old, k->u, k->u_old, k->r,
                                                                 k->z, k->partials, done);
             LAUNCH_CHECK(ctx);
@@ -383,6 +387,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (k->h_fl[F_DONE] || enq >= ctx->maxit) break;
     }
+    prof_collect(ctx);
     info[0] = (double)k->h_fl[F_ITERS];
     info[1] = (double)k->h_fl[F_CONV];
     info[2] = k->h_sc[S_NORM0] > 0 ? k->h_sc[S_NORM] / k->h_sc[S_NORM0] : 0.0;

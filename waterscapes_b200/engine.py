@@ -161,5 +161,12 @@ class Engine:
     def launch_count(self, reset=False):
         return int(self.lib.mpet_launch_count(self._ctx, int(reset)))
 
+    def profile(self, enable=-1):
+        """Read (and optionally reset/switch) the library's CUDA-event profile."""
+        out = (C.c_double * 16)()
+        self._ck(self.lib.mpet_profile(self._ctx, int(enable), out))
+        names = ["spmv", "pc", "vec", "assemble", "rhs"]
+        return {n: dict(ms=float(out[i]), count=int(out[8 + i])) for i, n in enumerate(names)}
+
     def device_bytes(self):
         return int(self.lib.mpet_device_bytes(self._ctx))

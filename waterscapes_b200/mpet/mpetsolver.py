@@ -299,12 +299,21 @@ class MPETSolver(object):
         for bc in bcs:
             bc.apply(A)
         self._sync_dirichlet(bcs)
-        solver = LUSolver(A, "mumps")
+        if self.params["direct_solver"]:
+            solver = LUSolver(A, "mumps")
+            krylov = solver.krylov
+        else:       # the reference's unreachable iterative recipe (mpetsolver.py:507), reference tolerance
+            self._ensure_prec()
+            krylov = PETScKrylovSolver("minres" if self._exchange_is_symmetric() else "gmres", "hypre_amg")
+            krylov.parameters.update(relative_tolerance=self.params["krylov_rtol"],
+                                     absolute_tolerance=self.params["krylov_atol"],
+                                     maximum_iterations=self.params["krylov_maxit"], nonzero_initial_guess=True)
         b = self._rhs(time, float(time), float(dt), theta, bcs)
         self.up.x.copy_(self.up_.x)               # initial guess; boundary entries are overwritten
-        niter = solver.solve(A, self.up.vector(), b)
+        krylov.set_operators(A, None)
+        niter = krylov.solve(self.up.vector(), b)
         self.solver_monitor.setdefault("niter", []).append(niter)
-        self.solver_monitor["last"] = solver.krylov.last_info
+        self.solver_monitor["last"] = krylov.last_info
 
     def solve_direct(self):
         """Generator twin of mpetsolver.py:382-462 (A assembled once, one solve per step)."""
