@@ -322,12 +322,18 @@ def main():
     e2e_value = total_dofs / (ms_e2e / args.steps / 1e3)
 
     peak, peak_src = measured_peak()
-    spmv_bytes = 12 * S["nnz"] + 20 * S["N"]
+    # algorithmic bytes of one node-blocked SpMV launch pair (DESIGN.md "SpMV"): every value once, one
+    # column index per NODE pair, row pointers, x read once + y written once in the padded layout
+    nint = 4 * S["N2"] + S["A"] * S["Nv"]
+    spmv_bytes = (8 * S["nnz"] + 4 * (S["nnz22"] + 2 * S["nnz21"] + S["nnz11"]) + 8 * S["N"]
+                  + 8 * (S["N2"] + S["Nv"]) + 16 * nint)
+    csr_equiv_bytes = 12 * S["nnz"] + 20 * S["N"]
     spmv_ms = prof["spmv"]["ms"] / max(1, prof["spmv"]["count"])
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_spmv_vec<32> (block-system CSR SpMV inside MINRES)",
+    roofline = {"bound": "hbm", "kernel": "k_spmv_block_u + k_spmv_block_p (node-blocked SpMV of the block system inside MINRES)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "csr_equivalent_gbs": csr_equiv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                 "avg_launch_ms": spmv_ms, "launches_timed": prof["spmv"]["count"],
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),

@@ -17,6 +17,7 @@
 // once per (mesh, dt) on the host in this translation unit on the small P1-sized matrices and is
 // uploaded; everything per-iteration is device code.
 #include "ctx.h"
+#include "layout.cuh"
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -24,131 +25,156 @@
 namespace {
 
 // =============================================================================== device kernels
-__device__ __forceinline__ double ldg_stream(const double* p) {
-    double r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ int32_t ldg_stream(const int32_t* p) {
-    int32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-
+// Vectors of a hierarchy are "W-wide": row r owns W consecutive doubles.  W = 4 for the displacement
+// block (three components + zero pad, solver-internal layout of layout.cuh: one 256-bit gather per
+// matrix entry serves all three right-hand sides), W = 1 for a pressure block.
 enum { EPI_RESID = 0, EPI_CHEB = 1 };
 
-// Fused SpMM + epilogue over NRHS vectors (leading dimension ld for every vector array):
+template <int W> struct Acc;
+template <> struct Acc<1> {
+    double v;
+    __device__ __forceinline__ void zero() { v = 0.0; }
+    __device__ __forceinline__ void fma_gather(double a, const double* x, int64_t c) { v += a * __ldg(x + c); }
+    template <int LANES> __device__ __forceinline__ void reduce() {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LANES);
+    }
+};
+template <> struct Acc<4> {
+    d4 v;
+    __device__ __forceinline__ void zero() { v.x = v.y = v.z = v.w = 0.0; }
+    __device__ __forceinline__ void fma_gather(double a, const double* x, int64_t c) {
+        const d4 g = ld256_gather(x + 4 * c);
+        v.x += a * g.x; v.y += a * g.y; v.z += a * g.z; v.w += a * g.w;
+    }
+    template <int LANES> __device__ __forceinline__ void reduce() {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, o, LANES);
+            v.y += __shfl_xor_sync(0xffffffffu, v.y, o, LANES);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, o, LANES);
+            v.w += __shfl_xor_sync(0xffffffffu, v.w, o, LANES);
+        }
+    }
+};
+
+// Fused SpMM + epilogue:
 //   EPI_RESID: out = b - A x
-//   EPI_CHEB : r = b - A x ; d = c1*d + c2*dinv*r ; xout = x + d
-template <int LANES, int NRHS, int EPI>
+//   EPI_CHEB : r = b - A x ; d = c1*d + c2*dinv*r ; out = x + d          (out must not alias x)
+template <int LANES, int W, int EPI>
 __global__ void __launch_bounds__(256)
 k_spmm_epi(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
            const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ b,
            double* __restrict__ out, double* __restrict__ d, const double* __restrict__ dinv, double c1,
-           double c2, int64_t ldx, int64_t ldb, int64_t ldo, int64_t ldd, const int* __restrict__ done) {
+           double c2, const int* __restrict__ done) {
     if (done && *done) return;
     const int lane = threadIdx.x & (LANES - 1);
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
     if (row >= nrows) return;
     const int32_t s = rowptr[row], e = rowptr[row + 1];
-    double sum[NRHS];
-#pragma unroll
-    for (int k = 0; k < NRHS; ++k) sum[k] = 0.0;
+    Acc<W> acc;
+    acc.zero();
     for (int32_t i = s + lane; i < e; i += LANES) {
-        double v = ldg_stream(vals + i);
-        int32_t c = ldg_stream(cols + i);
-#pragma unroll
-        for (int k = 0; k < NRHS; ++k) sum[k] += v * __ldg(x + k * ldx + c);
+        const double v = ldg_stream_f64(vals + i);
+        const int32_t c = ldg_stream_s32(cols + i);
+        acc.fma_gather(v, x, c);
     }
-#pragma unroll
-    for (int k = 0; k < NRHS; ++k) {
-        double r = sum[k];
-#pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o, LANES);
-        if (lane == 0) {
-            double res = b[k * ldb + row] - r;
-            if (EPI == EPI_RESID) {
-                out[k * ldo + row] = res;
-            } else {
-                double dn = c2 * dinv[row] * res;
-                if (c1 != 0.0) dn += c1 * d[k * ldd + row];
-                d[k * ldd + row] = dn;
-                out[k * ldo + row] = x[k * ldx + row] + dn;
+    acc.template reduce<LANES>();
+    if (lane != 0) return;
+    if constexpr (W == 1) {
+        const double res = b[row] - acc.v;
+        if (EPI == EPI_RESID) {
+            out[row] = res;
+        } else {
+            double dn = c2 * dinv[row] * res;
+            if (c1 != 0.0) dn += c1 * d[row];
+            d[row] = dn;
+            out[row] = x[row] + dn;
+        }
+    } else {
+        const d4 a = acc.v;
+        const d4 bb = ld256(b + 4 * row);
+        d4 res = {bb.x - a.x, bb.y - a.y, bb.z - a.z, bb.w - a.w};
+        if (EPI == EPI_RESID) {
+            st256(out + 4 * row, res);
+        } else {
+            const double s2 = c2 * dinv[row];
+            d4 dn = {s2 * res.x, s2 * res.y, s2 * res.z, s2 * res.w};
+            if (c1 != 0.0) {
+                const d4 dd = ld256(d + 4 * row);
+                dn.x += c1 * dd.x; dn.y += c1 * dd.y; dn.z += c1 * dd.z; dn.w += c1 * dd.w;
             }
+            st256(d + 4 * row, dn);
+            const d4 xr = ld256(x + 4 * row);
+            d4 o = {xr.x + dn.x, xr.y + dn.y, xr.z + dn.z, xr.w + dn.w};
+            st256(out + 4 * row, o);
         }
     }
 }
 
 // first Chebyshev step from a zero guess: d = c2 * dinv * b ; x = d
-template <int NRHS>
+template <int W>
 __global__ void k_cheb_first(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
-                             double c2, double* __restrict__ d, double* __restrict__ x, int64_t ldb,
-                             int64_t ldd, int64_t ldx, const int* __restrict__ done) {
+                             double c2, double* __restrict__ d, double* __restrict__ x,
+                             const int* __restrict__ done) {
     if (done && *done) return;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double di = dinv[i];
-#pragma unroll
-    for (int k = 0; k < NRHS; ++k) {
-        double v = c2 * di * b[k * ldb + i];
-        d[k * ldd + i] = v;
-        x[k * ldx + i] = v;
-    }
+    if (i >= n * W) return;
+    double v = c2 * dinv[i / W] * b[i];
+    d[i] = v;
+    x[i] = v;
 }
 
-template <int NRHS>
+template <int W>
 __global__ void k_dense_apply(int n, const double* __restrict__ inv, const double* __restrict__ b,
-                              double* __restrict__ x, int64_t ldb, int64_t ldx, const int* __restrict__ done) {
+                              double* __restrict__ x, const int* __restrict__ done) {
     if (done && *done) return;
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n) return;
-    double sum[NRHS];
+    double sum[W];
 #pragma unroll
-    for (int k = 0; k < NRHS; ++k) sum[k] = 0.0;
+    for (int k = 0; k < W; ++k) sum[k] = 0.0;
     for (int j = lane; j < n; j += 32) {
         double a = inv[(int64_t)row * n + j];
 #pragma unroll
-        for (int k = 0; k < NRHS; ++k) sum[k] += a * b[k * ldb + j];
+        for (int k = 0; k < W; ++k) sum[k] += a * b[(int64_t)j * W + k];
     }
 #pragma unroll
-    for (int k = 0; k < NRHS; ++k) {
+    for (int k = 0; k < W; ++k) {
         double r = sum[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-        if (lane == 0) x[k * ldx + row] = r;
+        if (lane == 0) x[(int64_t)row * W + k] = r;
     }
 }
 
-// Y (+)= alpha * M X for NRHS vectors, skipping when done
-template <int LANES, int NRHS>
+// y = M x (+ y) on W-wide vectors (restriction / prolongation / power iteration)
+template <int LANES, int W>
 __global__ void __launch_bounds__(256)
 k_spmm_plain(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
              const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-             int64_t ldx, int64_t ldy, double beta, const int* __restrict__ done) {
+             double beta, const int* __restrict__ done) {
     if (done && *done) return;
     const int lane = threadIdx.x & (LANES - 1);
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
     if (row >= nrows) return;
     const int32_t s = rowptr[row], e = rowptr[row + 1];
-    double sum[NRHS];
-#pragma unroll
-    for (int k = 0; k < NRHS; ++k) sum[k] = 0.0;
-    for (int32_t i = s + lane; i < e; i += LANES) {
-        double v = vals[i];
-        int32_t c = cols[i];
-#pragma unroll
-        for (int k = 0; k < NRHS; ++k) sum[k] += v * __ldg(x + k * ldx + c);
-    }
-#pragma unroll
-    for (int k = 0; k < NRHS; ++k) {
-        double r = sum[k];
-#pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o, LANES);
-        if (lane == 0) {
-            double* yp = y + k * ldy + row;
-            *yp = (beta == 0.0) ? r : r + beta * (*yp);
+    Acc<W> acc;
+    acc.zero();
+    for (int32_t i = s + lane; i < e; i += LANES) acc.fma_gather(vals[i], x, cols[i]);
+    acc.template reduce<LANES>();
+    if (lane != 0) return;
+    if constexpr (W == 1) {
+        double r = acc.v;
+        y[row] = (beta == 0.0) ? r : r + beta * y[row];
+    } else {
+        d4 r = acc.v;
+        if (beta != 0.0) {
+            const d4 yy = ld256(y + 4 * row);
+            r.x += beta * yy.x; r.y += beta * yy.y; r.z += beta * yy.z; r.w += beta * yy.w;
         }
+        st256(y + 4 * row, r);
     }
 }
 
@@ -415,39 +441,38 @@ const double kChebRatio = 4.0;    // smooth the upper [lambda_max / ratio, lambd
 const int64_t kCoarseMax = 300;
 const int kMaxLevels = 12;
 
-template <int NRHS, int EPI>
+template <int W, int EPI>
 void launch_epi(mpet_ctx* ctx, const DevCsr& M, const double* x, const double* b, double* out, double* d,
-                const double* dinv, double c1, double c2, int64_t ldx, int64_t ldb, int64_t ldo, int64_t ldd,
-                const int* done, cudaStream_t st) {
+                const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
     double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
     const int th = 256;
     if (mean > 20)
-        k_spmm_epi<32, NRHS, EPI><<<grid_for(M.nrows * 32, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, ldx, ldb, ldo, ldd, done);
+        k_spmm_epi<32, W, EPI><<<grid_for(M.nrows * 32, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
     else if (mean > 10)
-        k_spmm_epi<16, NRHS, EPI><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, ldx, ldb, ldo, ldd, done);
+        k_spmm_epi<16, W, EPI><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
     else
-        k_spmm_epi<8, NRHS, EPI><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, ldx, ldb, ldo, ldd, done);
+        k_spmm_epi<8, W, EPI><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
     LAUNCH_CHECK(ctx);
 }
 
-template <int NRHS>
-void launch_plain(mpet_ctx* ctx, const DevCsr& M, const double* x, double* y, int64_t ldx, int64_t ldy,
-                  double beta, const int* done, cudaStream_t st) {
+template <int W>
+void launch_plain(mpet_ctx* ctx, const DevCsr& M, const double* x, double* y, double beta, const int* done,
+                  cudaStream_t st) {
     double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
     const int th = 256;
     if (mean > 10)
-        k_spmm_plain<16, NRHS><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, ldx, ldy, beta, done);
+        k_spmm_plain<16, W><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, beta, done);
     else if (mean > 3)
-        k_spmm_plain<8, NRHS><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, ldx, ldy, beta, done);
+        k_spmm_plain<8, W><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, beta, done);
     else
-        k_spmm_plain<2, NRHS><<<grid_for(M.nrows * 2, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, ldx, ldy, beta, done);
+        k_spmm_plain<2, W><<<grid_for(M.nrows * 2, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, y, beta, done);
     LAUNCH_CHECK(ctx);
 }
 
 // Chebyshev smoothing on level L: x_out = S(b, x_in); x_in == nullptr means zero initial guess.
-template <int NRHS>
-void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, int64_t ldb, const double* x_in, int64_t ldxin,
-               double* x_out, int64_t ldxout, const int* done, cudaStream_t st) {
+template <int W>
+void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, double* x_out, const int* done,
+               cudaStream_t st) {
     const int64_t n = L.A.nrows;
     const double lmax = L.lambda_max, lmin = lmax / kChebRatio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
@@ -455,60 +480,52 @@ void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, int64_t ldb, const d
     double rho_old = 1.0 / sigma;
     double* buf[2] = {L.x, L.t};
     const double* cur = x_in;
-    int64_t ldcur = ldxin;
-    int steps = kChebDegree;
+    const int steps = kChebDegree;
     for (int k = 0; k < steps; ++k) {
         bool last = (k == steps - 1);
         double* dst = last ? x_out : buf[k & 1];
-        int64_t lddst = last ? ldxout : n;
-        bool bounce = last && cur == x_out;    // SpMM cannot run in place
-        if (bounce) { dst = buf[k & 1]; lddst = n; }
+        bool bounce = last && cur == x_out;    // the SpMM cannot run in place
+        if (bounce) dst = buf[k & 1];
         if (k == 0) {
             if (cur == nullptr) {
-                k_cheb_first<NRHS><<<grid_for(n, 256), 256, 0, st>>>(n, b, L.dinv, 1.0 / theta, L.r, dst, ldb, n, lddst, done);
+                k_cheb_first<W><<<grid_for(n * W, 256), 256, 0, st>>>(n, b, L.dinv, 1.0 / theta, L.r, dst, done);
                 LAUNCH_CHECK(ctx);
             } else {
-                launch_epi<NRHS, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, 0.0, 1.0 / theta, ldcur, ldb, lddst, n, done, st);
+                launch_epi<W, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, 0.0, 1.0 / theta, done, st);
             }
         } else {
             double rho = 1.0 / (2.0 * sigma - rho_old);
-            launch_epi<NRHS, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, rho * rho_old, 2.0 * rho / delta, ldcur, ldb, lddst, n, done, st);
+            launch_epi<W, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, rho * rho_old, 2.0 * rho / delta, done, st);
             rho_old = rho;
         }
-        if (bounce) {
-            for (int q = 0; q < NRHS; ++q)
-                CUDA_CHECK(cudaMemcpyAsync(x_out + q * ldxout, dst + q * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        }
+        if (bounce)
+            CUDA_CHECK(cudaMemcpyAsync(x_out, dst, sizeof(double) * n * W, cudaMemcpyDeviceToDevice, st));
         cur = dst;
-        ldcur = lddst;
     }
 }
 
-template <int NRHS>
-void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, int64_t ldb, double* x, int64_t ldx,
-            const int* done, cudaStream_t st) {
+template <int W>
+void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x, const int* done, cudaStream_t st) {
     AmgLevel& L = H.levels[lev];
     const int64_t n = L.A.nrows;
     if (lev == (int)H.levels.size() - 1) {
         if (H.coarse_inv) {
-            k_dense_apply<NRHS><<<grid_for((int64_t)n * 32, 256), 256, 0, st>>>((int)n, H.coarse_inv, b, x, ldb, ldx, done);
+            k_dense_apply<W><<<grid_for((int64_t)n * 32, 256), 256, 0, st>>>((int)n, H.coarse_inv, b, x, done);
             LAUNCH_CHECK(ctx);
         } else {
-            chebyshev<NRHS>(ctx, L, b, ldb, nullptr, 0, x, ldx, done, st);
+            chebyshev<W>(ctx, L, b, nullptr, x, done, st);
         }
         return;
     }
     AmgLevel& C = H.levels[lev + 1];
     const int64_t nc = C.A.nrows;
-    // pre-smooth from zero into L.b2 (kept in x), residual, restrict
-    chebyshev<NRHS>(ctx, L, b, ldb, nullptr, 0, x, ldx, done, st);
-    launch_epi<NRHS, EPI_RESID>(ctx, L.A, x, b, L.t, nullptr, nullptr, 0, 0, ldx, ldb, n, 0, done, st);
-    launch_plain<NRHS>(ctx, C.R, L.t, C.b, n, nc, 0.0, done, st);
-    double* xc = C.x + (int64_t)NRHS * nc;   // second half of the coarse x buffer holds the coarse solution
-    vcycle<NRHS>(ctx, H, lev + 1, C.b, nc, xc, nc, done, st);
-    launch_plain<NRHS>(ctx, C.P, xc, x, nc, ldx, 1.0, done, st);
-    // post-smooth in place: x_in = x (copy through the level buffers), final write back to x
-    chebyshev<NRHS>(ctx, L, b, ldb, x, ldx, x, ldx, done, st);
+    chebyshev<W>(ctx, L, b, nullptr, x, done, st);                                            // pre-smooth
+    launch_epi<W, EPI_RESID>(ctx, L.A, x, b, L.t, nullptr, nullptr, 0, 0, done, st);           // residual
+    launch_plain<W>(ctx, C.R, L.t, C.b, 0.0, done, st);                                        // restrict
+    double* xc = C.x + (int64_t)W * nc;   // second half of the coarse x buffer holds the coarse solution
+    vcycle<W>(ctx, H, lev + 1, C.b, xc, done, st);
+    launch_plain<W>(ctx, C.P, xc, x, 1.0, done, st);                                           // prolong + correct
+    chebyshev<W>(ctx, L, b, x, x, done, st);                                                   // post-smooth
 }
 
 void alloc_level_work(mpet_ctx* ctx, AmgLevel& L, int nrhs) {
@@ -540,7 +557,7 @@ double estimate_lambda_max(mpet_ctx* ctx, AmgLevel& L, cudaStream_t st) {
     CUDA_CHECK(cudaMemcpy(x, x0.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     double lam = 0;
     for (int it = 0; it < 20; ++it) {
-        launch_plain<1>(ctx, L.A, x, y, n, n, 0.0, nullptr, st);
+        launch_plain<1>(ctx, L.A, x, y, 0.0, nullptr, st);
         k_scale_by<<<grid_for(n, 256), 256, 0, st>>>(n, L.dinv, y);
         LAUNCH_CHECK(ctx);
         CUDA_CHECK(cudaMemcpyAsync(h.data(), y, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -673,7 +690,7 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
     // ---- displacement block
     {
         AmgHierarchy* H = new AmgHierarchy();
-        H->nrhs = 3;
+        H->nrhs = 4;   // W = 4: three components + pad
         AmgLevel L0;
         L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->mu, ctx->bc_mask, &L0.dinv, st);
         H->levels.push_back(L0);
@@ -703,12 +720,13 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// r, z in the solver-internal layout (layout.cuh)
 void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
-    vcycle<3>(ctx, *ctx->amg_u, 0, r, n2, z, n2, done, st);
+    vcycle<4>(ctx, *ctx->amg_u, 0, r, z, done, st);
     for (int i = 0; i < ctx->A; ++i) {
-        int64_t off = 3 * n2 + (int64_t)i * nv;
-        vcycle<1>(ctx, *ctx->amg_p[i], 0, r + off, nv, z + off, nv, done, st);
+        int64_t off = 4 * n2 + (int64_t)i * nv;
+        vcycle<1>(ctx, *ctx->amg_p[i], 0, r + off, z + off, done, st);
     }
 }
 

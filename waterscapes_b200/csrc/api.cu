@@ -13,6 +13,7 @@ void krylov_free(mpet_ctx* ctx);
 void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st);
 void pc_setup(mpet_ctx* ctx, cudaStream_t st);
 void pc_apply(mpet_ctx* ctx, const double* r, double* z, cudaStream_t st);
+void spmv_api(mpet_ctx* ctx, const double* x, double* y, cudaStream_t st);
 void amg_free(mpet_ctx* ctx);
 // dist.cu
 void dist_attach(mpet_ctx* ctx, const void* uid, int rank, int nranks);
@@ -294,7 +295,9 @@ int mpet_apply_dirichlet_rhs(mpet_ctx* ctx, double* b, void* stream) {
 int mpet_spmv(mpet_ctx* ctx, const double* x, double* y, void* stream) {
     MPET_TRY(ctx)
     MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run first");
-    csr_spmv(ctx, ctx->N, ctx->rowptr, ctx->cols, ctx->vals, x, y, 0.0, nullptr, as_stream(stream));
+    cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
+    spmv_api(ctx, x, y, as_stream(stream));
+    prof_end(ctx, PROF_VEC, pe, as_stream(stream));
     MPET_CATCH(ctx)
 }
 

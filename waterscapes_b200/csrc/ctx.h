@@ -97,6 +97,7 @@ struct mpet_ctx {
 
     // mesh / space
     int64_t Nv = 0, Ne = 0, N2 = 0, Nc = 0, N = 0, nnz = 0;
+    int64_t Nint = 0;            // 4*N2 + A*Nv: length of solver-internal vectors (layout.cuh)
     int A = 0;                   // networks
     int nloc = 0;
     double* coords = nullptr;    // [Nv*3] (library copy)
@@ -126,7 +127,10 @@ struct mpet_ctx {
     int64_t n_bc = 0;
     int32_t* bc_dofs = nullptr;
     double* bc_vals = nullptr;
-    uint8_t* bc_mask = nullptr;  // [N] 1 on Dirichlet rows
+    uint8_t* bc_mask = nullptr;  // [N] 1 on Dirichlet rows (API numbering)
+    uint8_t* bc_mask_int = nullptr;   // [Nint] same in the solver-internal layout
+    int32_t* bc_dofs_int = nullptr;   // [n_bc] internal indices of the Dirichlet dofs
+    double* scratch_int[2] = {nullptr, nullptr};   // [Nint] layout-conversion buffers
 
     // Krylov
     int method = 0, pc = 2, maxit = 10000, restart = 30;
@@ -194,5 +198,9 @@ void amg_free(mpet_ctx* ctx);
 void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
               const double* vals, const double* x, double* y, double beta, const uint8_t* rowmask,
               cudaStream_t st, const int* done = nullptr);
+void block_spmv(mpet_ctx* ctx, const double* x_int, double* y_int, const uint8_t* mask_int, const int* done,
+                cudaStream_t st);
+void to_internal(mpet_ctx* ctx, const double* src_api, double* dst_int, cudaStream_t st);
+void to_api(mpet_ctx* ctx, const double* src_int, double* dst_api, cudaStream_t st);
 void csr32_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, double* y, int64_t ldy,
                 int nrhs, double alpha, double beta, cudaStream_t st);

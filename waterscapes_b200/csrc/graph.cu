@@ -303,6 +303,7 @@ void build_space(mpet_ctx* ctx, cudaStream_t st) {
     const int64_t n2 = ctx->N2;
     ctx->N = 3 * n2 + A * nv;
     ctx->nloc = 30 + 4 * A;
+    ctx->Nint = 4 * n2 + (int64_t)A * nv;
     MPET_REQUIRE(ctx->N < 2147483647LL, "more than 2^31 dofs on one GPU");
 
     // ---- scalar node graphs with gather lists

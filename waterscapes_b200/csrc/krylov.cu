@@ -18,7 +18,7 @@
 #include <cmath>
 #include <vector>
 
-void scatter_bc_values(mpet_ctx* ctx, double* out, cudaStream_t st);   // rhs.cu
+void scatter_bc_values_int(mpet_ctx* ctx, double* out_int, cudaStream_t st);   // rhs.cu
 
 namespace {
 
@@ -268,7 +268,7 @@ __global__ void k_scale_copy(const double* __restrict__ src, double scale, int64
 struct KrylovWork {
     int64_t n = 0;
     double *r = nullptr, *z = nullptr, *v = nullptr, *v_old = nullptr, *u = nullptr, *u_old = nullptr,
-           *w1 = nullptr, *w2 = nullptr, *partials = nullptr, *sc = nullptr;
+           *w1 = nullptr, *w2 = nullptr, *xi = nullptr, *bi = nullptr, *partials = nullptr, *sc = nullptr;
     int* fl = nullptr;
     double* basis = nullptr;   // GMRES: (restart + 1) vectors
     int basis_m = 0;
@@ -278,12 +278,12 @@ struct KrylovWork {
 };
 
 static KrylovWork* get_work(mpet_ctx* ctx) {
-    if (ctx->kw && ctx->kw->n == ctx->N) return ctx->kw;
+    if (ctx->kw && ctx->kw->n == ctx->Nint) return ctx->kw;
     MPET_REQUIRE(ctx->kw == nullptr, "context size changed");
     KrylovWork* k = new KrylovWork();
-    k->n = ctx->N;
-    double** vecs[] = {&k->r, &k->z, &k->v, &k->v_old, &k->u, &k->u_old, &k->w1, &k->w2};
-    for (auto p : vecs) *p = dev_alloc<double>(ctx, ctx->N);
+    k->n = ctx->Nint;     // all Krylov vectors live in the solver-internal layout (layout.cuh)
+    double** vecs[] = {&k->r, &k->z, &k->v, &k->v_old, &k->u, &k->u_old, &k->w1, &k->w2, &k->xi, &k->bi};
+    for (auto p : vecs) *p = dev_alloc<double>(ctx, ctx->Nint);
     k->partials = dev_alloc<double>(ctx, (int64_t)kRedBlocks * 8);
     k->sc = dev_alloc<double>(ctx, S_COUNT);
     k->fl = dev_alloc<int>(ctx, F_COUNT);
@@ -305,17 +305,22 @@ void krylov_free(mpet_ctx* ctx) {
 void pc_setup(mpet_ctx* ctx, cudaStream_t st) {
     MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run before mpet_pc_setup");
     if (ctx->pc == 1) {
-        if (!ctx->jac_dinv) ctx->jac_dinv = dev_alloc<double>(ctx, ctx->N);
+        if (!ctx->jac_dinv) ctx->jac_dinv = dev_alloc<double>(ctx, ctx->Nint);
+        double* tmp = nullptr;
+        CUDA_CHECK(cudaMalloc(&tmp, sizeof(double) * ctx->N));
         k_abs_diag_inv<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N, ctx->rowptr, ctx->cols, ctx->vals,
-                                                              ctx->bc_mask, ctx->jac_dinv);
+                                                              ctx->bc_mask, tmp);
         LAUNCH_CHECK(ctx);
+        to_internal(ctx, tmp, ctx->jac_dinv, st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(tmp);
     } else if (ctx->pc == 2) {
         amg_setup(ctx, st);
     }
 }
 
 static void pc_apply_flag(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
-    const int64_t n = ctx->N;
+    const int64_t n = ctx->Nint;   // r, z: solver-internal layout
     if (ctx->pc == 0) {
         CUDA_CHECK(cudaMemcpyAsync(z, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     } else if (ctx->pc == 1) {
@@ -328,28 +333,46 @@ static void pc_apply_flag(mpet_ctx* ctx, const double* r, double* z, const int* 
     }
 }
 
-void pc_apply(mpet_ctx* ctx, const double* r, double* z, cudaStream_t st) { pc_apply_flag(ctx, r, z, nullptr, st); }
+static void ensure_scratch(mpet_ctx* ctx) {
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->scratch_int[i]) ctx->scratch_int[i] = dev_alloc<double>(ctx, ctx->Nint);
+}
+
+// API-layout entry points (tests / measurement): convert, run the production kernels, convert back
+void pc_apply(mpet_ctx* ctx, const double* r, double* z, cudaStream_t st) {
+    ensure_scratch(ctx);
+    to_internal(ctx, r, ctx->scratch_int[0], st);
+    pc_apply_flag(ctx, ctx->scratch_int[0], ctx->scratch_int[1], nullptr, st);
+    to_api(ctx, ctx->scratch_int[1], z, st);
+}
+
+void spmv_api(mpet_ctx* ctx, const double* x, double* y, cudaStream_t st) {
+    ensure_scratch(ctx);
+    to_internal(ctx, x, ctx->scratch_int[0], st);
+    block_spmv(ctx, ctx->scratch_int[0], ctx->scratch_int[1], nullptr, nullptr, st);
+    to_api(ctx, ctx->scratch_int[1], y, st);
+}
 
 static void dot_to(mpet_ctx* ctx, KrylovWork* k, const double* a, const double* b, const int* done, cudaStream_t st) {
     k_dot_partial<<<kRedBlocks, kRedThreads, 0, st>>>(a, b, k->n, k->partials, done);
     LAUNCH_CHECK(ctx);
 }
 
-static void initial_residual(mpet_ctx* ctx, KrylovWork* k, const double* b, double* x, cudaStream_t st) {
-    // x carries the Dirichlet values; r = b - A x on free rows, 0 on Dirichlet rows
-    if (ctx->n_bc > 0) {
-        scatter_bc_values(ctx, x, st);
-    }
-    csr_spmv(ctx, ctx->N, ctx->rowptr, ctx->cols, ctx->vals, x, k->v, 0.0, nullptr, st);
-    k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(b, k->v, ctx->n_bc > 0 ? ctx->bc_mask : nullptr, k->n, k->r);
+// xi (internal layout) carries the Dirichlet values; r = b - A x on free rows, 0 on Dirichlet rows
+static void initial_residual(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
+    if (ctx->n_bc > 0) scatter_bc_values_int(ctx, k->xi, st);
+    block_spmv(ctx, k->xi, k->v, nullptr, nullptr, st);
+    k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr, k->n, k->r);
     LAUNCH_CHECK(ctx);
 }
 
 static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
     KrylovWork* k = get_work(ctx);
     const int64_t n = k->n;
-    const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask : nullptr;
-    initial_residual(ctx, k, b, x, st);
+    const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
+    to_internal(ctx, b, k->bi, st);
+    to_internal(ctx, x, k->xi, st);
+    initial_residual(ctx, k, st);
     pc_apply_flag(ctx, k->r, k->z, nullptr, st);
     dot_to(ctx, k, k->r, k->z, nullptr, st);
     k_minres_init<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, ctx->rtol, ctx->atol, ctx->maxit, k->sc, k->fl);
@@ -363,7 +386,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     while (true) {
         for (int q = 0; q < check_every && enq < ctx->maxit; ++q, ++enq) {
             cudaEvent_t pe = prof_begin(ctx, st);
-            csr_spmv(ctx, n, ctx->rowptr, ctx->cols, ctx->vals, k->u, k->r, 0.0, mask, st, done);
+            block_spmv(ctx, k->u, k->r, mask, done, st);
             prof_end(ctx, PROF_SPMV, pe, st);
             dot_to(ctx, k, k->r, k->u, done, st);
             k_minres_alpha<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
@@ -376,7 +399,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
             LAUNCH_CHECK(ctx);
             k_minres_rotate<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
             LAUNCH_CHECK(ctx);
-            k_minres_finalize<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, x, k->w1, k->w2, k->v, k->v_old, k->u,
+            k_minres_finalize<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->xi, k->w1, k->w2, k->v, k->v_old, k->u,
                                                                 k->u_old, k->r, k->z, done);
             LAUNCH_CHECK(ctx);
             k_commit<<<1, 1, 0, st>>>(k->fl);
@@ -387,6 +410,8 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (k->h_fl[F_DONE] || enq >= ctx->maxit) break;
     }
+    to_api(ctx, k->xi, x, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
     prof_collect(ctx);
     info[0] = (double)k->h_fl[F_ITERS];
     info[1] = (double)k->h_fl[F_CONV];
@@ -423,14 +448,16 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         k->basis = dev_alloc<double>(ctx, (int64_t)(m + 1) * n);
         k->basis_m = m;
     }
-    const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask : nullptr;
+    const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
     double* V = k->basis;
+    to_internal(ctx, b, k->bi, st);
+    to_internal(ctx, x, k->xi, st);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
     int iters = 0;
     bool converged = false;
     double norm0 = -1, norm = 0, tol = 0;
     while (!converged && iters < ctx->maxit) {
-        initial_residual(ctx, k, b, x, st);
+        initial_residual(ctx, k, st);
         pc_apply_flag(ctx, k->r, k->z, nullptr, st);
         dot_to(ctx, k, k->z, k->z, nullptr, st);
         k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev);
@@ -449,7 +476,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         int j = 0;
         for (; j < m && iters < ctx->maxit; ++j) {
             double* w = V + (int64_t)(j + 1) * n;
-            csr_spmv(ctx, n, ctx->rowptr, ctx->cols, ctx->vals, V + (int64_t)j * n, k->r, 0.0, mask, st);
+            block_spmv(ctx, V + (int64_t)j * n, k->r, mask, nullptr, st);
             pc_apply_flag(ctx, k->r, w, nullptr, st);
             // classical Gram-Schmidt, two passes (CGS2)
             multidot(ctx, k, V, j + 1, w, k->hdev, 0, st);
@@ -497,12 +524,14 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         }
         if (jj > 0) {
             CUDA_CHECK(cudaMemcpyAsync(k->hdev, y.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, st));
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, jj, k->hdev, 1.0, n, x);
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, jj, k->hdev, 1.0, n, k->xi);
             LAUNCH_CHECK(ctx);
             CUDA_CHECK(cudaStreamSynchronize(st));
         }
         if (jj == 0) break;
     }
+    to_api(ctx, k->xi, x, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
     info[0] = iters;
     info[1] = converged ? 1.0 : 0.0;
     info[2] = norm0 > 0 ? norm / norm0 : 0.0;

@@ -10,6 +10,7 @@
 //                     modifies A: it masks rows on the fly (spmv.cu).
 //  * k_scatter_vals : bc.apply(b)  (mpetsolver.py:375-376,452-453).
 #include "ctx.h"
+#include "layout.cuh"
 
 namespace {
 
@@ -95,9 +96,14 @@ __global__ void k_scatter_vals(const int32_t* __restrict__ idx, const double* __
     if (i < n) out[idx[i]] = v[i];
 }
 
-__global__ void k_set_mask(const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ mask) {
+__global__ void k_set_mask(const int32_t* __restrict__ idx, int64_t n, int64_t n2, uint8_t* __restrict__ mask,
+                           uint8_t* __restrict__ mask_int, int32_t* __restrict__ idx_int) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) mask[idx[i]] = 1;
+    if (i >= n) return;
+    mask[idx[i]] = 1;
+    int64_t j = api_to_internal(idx[i], n2);
+    mask_int[j] = 1;
+    idx_int[i] = (int32_t)j;
 }
 
 // A[row, col] += val for unique (row, col) pairs that exist in the pattern (binary search per entry)
@@ -166,8 +172,11 @@ void export_values(mpet_ctx* ctx, int which, double* out, cudaStream_t st) {
 }
 
 void set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, cudaStream_t st) {
-    if (ctx->bc_dofs) { dev_free(ctx, ctx->bc_dofs); dev_free(ctx, ctx->bc_vals); }
+    if (ctx->bc_dofs) { dev_free(ctx, ctx->bc_dofs); dev_free(ctx, ctx->bc_vals); dev_free(ctx, ctx->bc_dofs_int); }
     if (!ctx->bc_mask) ctx->bc_mask = dev_alloc<uint8_t>(ctx, ctx->N);
+    if (!ctx->bc_mask_int) ctx->bc_mask_int = dev_alloc<uint8_t>(ctx, ctx->Nint);
+    ctx->bc_dofs_int = dev_alloc<int32_t>(ctx, n);
+    CUDA_CHECK(cudaMemsetAsync(ctx->bc_mask_int, 0, ctx->Nint, st));
     ctx->n_bc = n;
     ctx->bc_dofs = dev_alloc<int32_t>(ctx, n);
     ctx->bc_vals = dev_alloc<double>(ctx, n);
@@ -175,9 +184,16 @@ void set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, cudaStrea
     CUDA_CHECK(cudaMemsetAsync(ctx->bc_vals, 0, sizeof(double) * (n > 0 ? n : 1), st));
     CUDA_CHECK(cudaMemsetAsync(ctx->bc_mask, 0, ctx->N, st));
     if (n > 0) {
-        k_set_mask<<<grid_for(n, 256), 256, 0, st>>>(ctx->bc_dofs, n, ctx->bc_mask);
+        k_set_mask<<<grid_for(n, 256), 256, 0, st>>>(ctx->bc_dofs, n, ctx->N2, ctx->bc_mask, ctx->bc_mask_int,
+                                                     ctx->bc_dofs_int);
         LAUNCH_CHECK(ctx);
     }
+}
+
+void scatter_bc_values_int(mpet_ctx* ctx, double* out_int, cudaStream_t st) {
+    if (ctx->n_bc == 0) return;
+    k_scatter_vals<<<grid_for(ctx->n_bc, 256), 256, 0, st>>>(ctx->bc_dofs_int, ctx->bc_vals, ctx->n_bc, out_int);
+    LAUNCH_CHECK(ctx);
 }
 
 void scatter_bc_values(mpet_ctx* ctx, double* out, cudaStream_t st) {

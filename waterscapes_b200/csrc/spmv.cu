@@ -10,6 +10,7 @@
 // vector, gathered through the read-only path, keeps L1/L2 to itself; partial sums are combined with
 // warp shuffles in a fixed order (deterministic).
 #include "ctx.h"
+#include "layout.cuh"
 
 namespace {
 
@@ -114,6 +115,165 @@ k_spmm32(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------ node-blocked SpMV
+// y = A x on the block system, vectors in the solver-internal layout (layout.cuh).  The kernels run
+// over the SCALAR node graphs: a P2 node pair (a, b) owns the 3x3 values A[(k,a),(l,b)], which sit in
+// the ordinary CSR value array at rowptr[k*N2+a] + l*deg22(a) + j.  One warp handles node a (its three
+// rows): lane j streams the nine values (coalesced across lanes for each (k,l)), reads ONE column
+// index and gathers the neighbour's displacement with ONE 256-bit load.  Bytes per node pair:
+// 72 (values) + 4 (index) instead of 108 for scalar CSR, and 1 gather wavefront instead of 9.
+template <int NA>
+__global__ void __launch_bounds__(256)
+k_spmv_block_u(int64_t n2, int64_t nv, const int32_t* __restrict__ rp22, const int32_t* __restrict__ col22,
+               const int32_t* __restrict__ rp21, const int32_t* __restrict__ col21,
+               const int64_t* __restrict__ rowptr, const double* __restrict__ vals,
+               const double* __restrict__ x, double* __restrict__ y, const uint8_t* __restrict__ mask,
+               const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t a = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= n2) return;
+    const int32_t e0 = rp22[a], d22 = rp22[a + 1] - e0;
+    const int32_t f0 = rp21[a], d21 = rp21[a + 1] - f0;
+    const double* v0 = vals + rowptr[a];
+    const double* v1 = vals + rowptr[n2 + a];
+    const double* v2 = vals + rowptr[2 * n2 + a];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    for (int32_t j = lane; j < d22; j += 32) {
+        const int32_t c = ldg_stream_s32(col22 + e0 + j);
+        // nine independent streaming loads are in flight before the dependent gather
+        const double a00 = ldg_stream_f64(v0 + j), a01 = ldg_stream_f64(v0 + d22 + j), a02 = ldg_stream_f64(v0 + 2 * d22 + j);
+        const double a10 = ldg_stream_f64(v1 + j), a11 = ldg_stream_f64(v1 + d22 + j), a12 = ldg_stream_f64(v1 + 2 * d22 + j);
+        const double a20 = ldg_stream_f64(v2 + j), a21 = ldg_stream_f64(v2 + d22 + j), a22 = ldg_stream_f64(v2 + 2 * d22 + j);
+        const d4 xb = ld256_gather(x + 4 * (int64_t)c);
+        acc0 += a00 * xb.x + a01 * xb.y + a02 * xb.z;
+        acc1 += a10 * xb.x + a11 * xb.y + a12 * xb.z;
+        acc2 += a20 * xb.x + a21 * xb.y + a22 * xb.z;
+    }
+    if (NA > 0) {
+        const double* p = x + 4 * n2;
+        const int64_t off = 3 * (int64_t)d22;
+        for (int32_t j = lane; j < d21; j += 32) {
+            const int32_t v = ldg_stream_s32(col21 + f0 + j);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const double pv = __ldg(p + (int64_t)i * nv + v);
+                const int64_t o = off + (int64_t)i * d21 + j;
+                acc0 += ldg_stream_f64(v0 + o) * pv;
+                acc1 += ldg_stream_f64(v1 + o) * pv;
+                acc2 += ldg_stream_f64(v2 + o) * pv;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+    }
+    if (lane == 0) {
+        d4 out = {acc0, acc1, acc2, 0.0};
+        if (mask) {
+            const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + 4 * a);
+            if (m) {
+                const d4 xa = ld256(x + 4 * a);
+                if (m & 0x000000ffu) out.x = xa.x;
+                if (m & 0x0000ff00u) out.y = xa.y;
+                if (m & 0x00ff0000u) out.z = xa.z;
+            }
+        }
+        st256(y + 4 * a, out);
+    }
+}
+
+// pressure rows: one warp per vertex handles the rows of all NA networks
+template <int NA>
+__global__ void __launch_bounds__(256)
+k_spmv_block_p(int64_t n2, int64_t nv, const int32_t* __restrict__ rp12, const int32_t* __restrict__ col12,
+               const int32_t* __restrict__ rp11, const int32_t* __restrict__ col11,
+               const int64_t* __restrict__ rowptr, const double* __restrict__ vals,
+               const double* __restrict__ x, double* __restrict__ y, const uint8_t* __restrict__ mask,
+               const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= nv) return;
+    const int32_t g0 = rp12[v], d12 = rp12[v + 1] - g0;
+    const int32_t h0 = rp11[v], d11 = rp11[v + 1] - h0;
+    const double* vb[NA];
+    double acc[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        vb[i] = vals + rowptr[3 * n2 + (int64_t)i * nv + v];
+        acc[i] = 0.0;
+    }
+    for (int32_t j = lane; j < d12; j += 32) {
+        const int32_t a = ldg_stream_s32(col12 + g0 + j);
+        double w[NA][3];
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[i][k] = ldg_stream_f64(vb[i] + (int64_t)k * d12 + j);
+        const d4 xa = ld256_gather(x + 4 * (int64_t)a);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc[i] += w[i][0] * xa.x + w[i][1] * xa.y + w[i][2] * xa.z;
+    }
+    const double* p = x + 4 * n2;
+    const int64_t off = 3 * (int64_t)d12;
+    for (int32_t j = lane; j < d11; j += 32) {
+        const int32_t vp = ldg_stream_s32(col11 + h0 + j);
+#pragma unroll
+        for (int jj = 0; jj < NA; ++jj) {
+            const double pj = __ldg(p + (int64_t)jj * nv + vp);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) acc[i] += ldg_stream_f64(vb[i] + off + (int64_t)jj * d11 + j) * pj;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        double r = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) {
+            const int64_t idx = 4 * n2 + (int64_t)i * nv + v;
+            y[idx] = (mask && mask[idx]) ? x[idx] : r;
+        }
+    }
+}
+
+__global__ void k_to_internal(int64_t n2, int64_t npress, const double* __restrict__ src, double* __restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 4 * n2 + npress) return;
+    if (i < 4 * n2) {
+        int64_t a = i >> 2;
+        int k = (int)(i & 3);
+        dst[i] = k < 3 ? src[k * n2 + a] : 0.0;
+    } else {
+        dst[i] = src[i - n2];
+    }
+}
+
+__global__ void k_to_api(int64_t n2, int64_t n, const double* __restrict__ src, double* __restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[api_to_internal(i, n2)];
+}
+
+template <int NA>
+void launch_block(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done, cudaStream_t st) {
+    const int th = 256;
+    k_spmv_block_u<NA><<<grid_for(ctx->N2 * 32, th), th, 0, st>>>(ctx->N2, ctx->Nv, ctx->g22.rowptr, ctx->g22.col,
+                                                                  ctx->g21.rowptr, ctx->g21.col, ctx->rowptr,
+                                                                  ctx->vals, x, y, mask, done);
+    LAUNCH_CHECK(ctx);
+    if (NA > 0) {
+        k_spmv_block_p<(NA > 0 ? NA : 1)><<<grid_for(ctx->Nv * 32, th), th, 0, st>>>(
+            ctx->N2, ctx->Nv, ctx->g12.rowptr, ctx->g12.col, ctx->g11.rowptr, ctx->g11.col, ctx->rowptr, ctx->vals,
+            x, y, mask, done);
+        LAUNCH_CHECK(ctx);
+    }
+}
+
 template <int NRHS>
 void launch_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, double* y, int64_t ldy,
                  double alpha, double beta, cudaStream_t st) {
@@ -152,4 +312,30 @@ void csr32_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, do
     if (nrhs == 1) launch_spmm<1>(ctx, M, x, ldx, y, ldy, alpha, beta, st);
     else if (nrhs == 3) launch_spmm<3>(ctx, M, x, ldx, y, ldy, alpha, beta, st);
     else MPET_REQUIRE(false, "csr32_spmm: nrhs must be 1 or 3");
+}
+
+void block_spmv(mpet_ctx* ctx, const double* x_int, double* y_int, const uint8_t* mask_int, const int* done,
+                cudaStream_t st) {
+    switch (ctx->A) {
+        case 0: launch_block<0>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 1: launch_block<1>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 2: launch_block<2>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 3: launch_block<3>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 4: launch_block<4>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 5: launch_block<5>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 6: launch_block<6>(ctx, x_int, y_int, mask_int, done, st); break;
+        case 7: launch_block<7>(ctx, x_int, y_int, mask_int, done, st); break;
+        default: launch_block<8>(ctx, x_int, y_int, mask_int, done, st); break;
+    }
+}
+
+void to_internal(mpet_ctx* ctx, const double* src_api, double* dst_int, cudaStream_t st) {
+    int64_t n = 4 * ctx->N2 + (int64_t)ctx->A * ctx->Nv;
+    k_to_internal<<<grid_for(n, 256), 256, 0, st>>>(ctx->N2, (int64_t)ctx->A * ctx->Nv, src_api, dst_int);
+    LAUNCH_CHECK(ctx);
+}
+
+void to_api(mpet_ctx* ctx, const double* src_int, double* dst_api, cudaStream_t st) {
+    k_to_api<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N2, ctx->N, src_int, dst_api);
+    LAUNCH_CHECK(ctx);
 }
