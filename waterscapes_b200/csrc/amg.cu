@@ -72,6 +72,19 @@ k_spmm_epi(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __r
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
     if (row >= nrows) return;
     const int32_t s = rowptr[row], e = rowptr[row + 1];
+    // the row-wise operands of the epilogue do not depend on the SpMM: issue their loads first so that
+    // they travel together with the matrix stream instead of after the reduction
+    double eb1 = 0, ed1 = 0, ex1 = 0, edi = 0;
+    d4 eb4 = {0, 0, 0, 0}, ed4 = {0, 0, 0, 0}, ex4 = {0, 0, 0, 0};
+    if (lane == 0) {
+        if constexpr (W == 1) {
+            eb1 = b[row];
+            if (EPI == EPI_CHEB) { edi = dinv[row]; ex1 = x[row]; if (c1 != 0.0) ed1 = d[row]; }
+        } else {
+            eb4 = ld256(b + 4 * row);
+            if (EPI == EPI_CHEB) { edi = dinv[row]; ex4 = ld256(x + 4 * row); if (c1 != 0.0) ed4 = ld256(d + 4 * row); }
+        }
+    }
     Acc<W> acc;
     acc.zero();
     for (int32_t i = s + lane; i < e; i += LANES) {
@@ -82,31 +95,24 @@ k_spmm_epi(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __r
     acc.template reduce<LANES>();
     if (lane != 0) return;
     if constexpr (W == 1) {
-        const double res = b[row] - acc.v;
+        const double res = eb1 - acc.v;
         if (EPI == EPI_RESID) {
             out[row] = res;
         } else {
-            double dn = c2 * dinv[row] * res;
-            if (c1 != 0.0) dn += c1 * d[row];
+            double dn = c2 * edi * res + c1 * ed1;
             d[row] = dn;
-            out[row] = x[row] + dn;
+            out[row] = ex1 + dn;
         }
     } else {
         const d4 a = acc.v;
-        const d4 bb = ld256(b + 4 * row);
-        d4 res = {bb.x - a.x, bb.y - a.y, bb.z - a.z, bb.w - a.w};
+        d4 res = {eb4.x - a.x, eb4.y - a.y, eb4.z - a.z, eb4.w - a.w};
         if (EPI == EPI_RESID) {
             st256(out + 4 * row, res);
         } else {
-            const double s2 = c2 * dinv[row];
-            d4 dn = {s2 * res.x, s2 * res.y, s2 * res.z, s2 * res.w};
-            if (c1 != 0.0) {
-                const d4 dd = ld256(d + 4 * row);
-                dn.x += c1 * dd.x; dn.y += c1 * dd.y; dn.z += c1 * dd.z; dn.w += c1 * dd.w;
-            }
+            const double s2 = c2 * edi;
+            d4 dn = {s2 * res.x + c1 * ed4.x, s2 * res.y + c1 * ed4.y, s2 * res.z + c1 * ed4.z, s2 * res.w + c1 * ed4.w};
             st256(d + 4 * row, dn);
-            const d4 xr = ld256(x + 4 * row);
-            d4 o = {xr.x + dn.x, xr.y + dn.y, xr.z + dn.z, xr.w + dn.w};
+            d4 o = {ex4.x + dn.x, ex4.y + dn.y, ex4.z + dn.z, ex4.w + dn.w};
             st256(out + 4 * row, o);
         }
     }
@@ -446,9 +452,9 @@ void launch_epi(mpet_ctx* ctx, const DevCsr& M, const double* x, const double* b
                 const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
     double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
     const int th = 256;
-    if (mean > 20)
+    if (mean > 48)
         k_spmm_epi<32, W, EPI><<<grid_for(M.nrows * 32, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
-    else if (mean > 10)
+    else if (mean > 20)
         k_spmm_epi<16, W, EPI><<<grid_for(M.nrows * 16, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
     else
         k_spmm_epi<8, W, EPI><<<grid_for(M.nrows * 8, th), th, 0, st>>>(M.nrows, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);

@@ -421,17 +421,17 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
 }
 
 // ---------------------------------------------------------------------------------- GMRES(m)
-static void multidot(mpet_ctx* ctx, KrylovWork* k, const double* V, int nv, const double* w, double* hdev,
-                     int accumulate, cudaStream_t st) {
+static void multidot(mpet_ctx* ctx, KrylovWork* k, const double* V, int64_t ldv, int nv, const double* w,
+                     double* hdev, int accumulate, cudaStream_t st) {
     const int G = 296;
     for (int k0 = 0; k0 < nv; k0 += 4) {
         int c = std::min(4, nv - k0);
-        const double* Vk = V + (int64_t)k0 * k->n;
+        const double* Vk = V + (int64_t)k0 * ldv;
         switch (c) {
-            case 1: k_multidot<1><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
-            case 2: k_multidot<2><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
-            case 3: k_multidot<3><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
-            default: k_multidot<4><<<G, kRedThreads, 0, st>>>(Vk, k->n, w, k->n, k->partials); break;
+            case 1: k_multidot<1><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
+            case 2: k_multidot<2><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
+            case 3: k_multidot<3><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
+            default: k_multidot<4><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
         }
         LAUNCH_CHECK(ctx);
         k_multifinal<<<c, kRedThreads, 0, st>>>(k->partials, G, hdev + k0, accumulate);
@@ -444,8 +444,9 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     const int64_t n = k->n;
     const int m = ctx->restart;
     MPET_REQUIRE(m >= 1 && m <= 120, "GMRES restart must be in 1..120");
+    const int64_t ldv = (n + 3) & ~(int64_t)3;   // 32-byte aligned basis vectors (256-bit loads in block_spmv)
     if (k->basis_m < m) {
-        k->basis = dev_alloc<double>(ctx, (int64_t)(m + 1) * n);
+        k->basis = dev_alloc<double>(ctx, (int64_t)(m + 1) * ldv);
         k->basis_m = m;
     }
     const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
@@ -475,15 +476,15 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         g[0] = beta;
         int j = 0;
         for (; j < m && iters < ctx->maxit; ++j) {
-            double* w = V + (int64_t)(j + 1) * n;
-            block_spmv(ctx, V + (int64_t)j * n, k->r, mask, nullptr, st);
+            double* w = V + (int64_t)(j + 1) * ldv;
+            block_spmv(ctx, V + (int64_t)j * ldv, k->r, mask, nullptr, st);
             pc_apply_flag(ctx, k->r, w, nullptr, st);
             // classical Gram-Schmidt, two passes (CGS2)
-            multidot(ctx, k, V, j + 1, w, k->hdev, 0, st);
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, j + 1, k->hdev, -1.0, n, w);
+            multidot(ctx, k, V, ldv, j + 1, w, k->hdev, 0, st);
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev, -1.0, n, w);
             LAUNCH_CHECK(ctx);
-            multidot(ctx, k, V, j + 1, w, k->hdev + 128, 0, st);
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, j + 1, k->hdev + 128, -1.0, n, w);
+            multidot(ctx, k, V, ldv, j + 1, w, k->hdev + 128, 0, st);
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev + 128, -1.0, n, w);
             LAUNCH_CHECK(ctx);
             dot_to(ctx, k, w, w, nullptr, st);
             k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev + j + 1);
@@ -524,7 +525,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         }
         if (jj > 0) {
             CUDA_CHECK(cudaMemcpyAsync(k->hdev, y.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, st));
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, n, jj, k->hdev, 1.0, n, k->xi);
+            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, jj, k->hdev, 1.0, n, k->xi);
             LAUNCH_CHECK(ctx);
             CUDA_CHECK(cudaStreamSynchronize(st));
         }
