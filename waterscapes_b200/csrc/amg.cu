@@ -448,8 +448,12 @@ const int64_t kCoarseMax = 300;
 const int kMaxLevels = 12;
 
 template <int W, int EPI>
-void launch_epi(mpet_ctx* ctx, const DevCsr& M, const double* x, const double* b, double* out, double* d,
-                const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
+void launch_epi(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const double* x, const double* b, double* out,
+                double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
+    if (plan.nchunks > 0) {
+        staged_spmm(ctx, W, EPI, plan, M, x, b, out, d, dinv, c1, c2, done, st);
+        return;
+    }
     double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
     const int th = 256;
     if (mean > 48)
@@ -462,8 +466,12 @@ void launch_epi(mpet_ctx* ctx, const DevCsr& M, const double* x, const double* b
 }
 
 template <int W>
-void launch_plain(mpet_ctx* ctx, const DevCsr& M, const double* x, double* y, double beta, const int* done,
-                  cudaStream_t st) {
+void launch_plain(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const double* x, double* y, double beta,
+                  const int* done, cudaStream_t st) {
+    if (plan.nchunks > 0) {
+        staged_spmm(ctx, W, 2, plan, M, x, nullptr, y, nullptr, nullptr, beta, 0.0, done, st);
+        return;
+    }
     double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
     const int th = 256;
     if (mean > 10)
@@ -497,11 +505,11 @@ void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, 
                 k_cheb_first<W><<<grid_for(n * W, 256), 256, 0, st>>>(n, b, L.dinv, 1.0 / theta, L.r, dst, done);
                 LAUNCH_CHECK(ctx);
             } else {
-                launch_epi<W, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, 0.0, 1.0 / theta, done, st);
+                launch_epi<W, EPI_CHEB>(ctx, L.A, L.planA, cur, b, dst, L.r, L.dinv, 0.0, 1.0 / theta, done, st);
             }
         } else {
             double rho = 1.0 / (2.0 * sigma - rho_old);
-            launch_epi<W, EPI_CHEB>(ctx, L.A, cur, b, dst, L.r, L.dinv, rho * rho_old, 2.0 * rho / delta, done, st);
+            launch_epi<W, EPI_CHEB>(ctx, L.A, L.planA, cur, b, dst, L.r, L.dinv, rho * rho_old, 2.0 * rho / delta, done, st);
             rho_old = rho;
         }
         if (bounce)
@@ -526,11 +534,11 @@ void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x,
     AmgLevel& C = H.levels[lev + 1];
     const int64_t nc = C.A.nrows;
     chebyshev<W>(ctx, L, b, nullptr, x, done, st);                                            // pre-smooth
-    launch_epi<W, EPI_RESID>(ctx, L.A, x, b, L.t, nullptr, nullptr, 0, 0, done, st);           // residual
-    launch_plain<W>(ctx, C.R, L.t, C.b, 0.0, done, st);                                        // restrict
+    launch_epi<W, EPI_RESID>(ctx, L.A, L.planA, x, b, L.t, nullptr, nullptr, 0, 0, done, st);           // residual
+    launch_plain<W>(ctx, C.R, C.planR, L.t, C.b, 0.0, done, st);                                        // restrict
     double* xc = C.x + (int64_t)W * nc;   // second half of the coarse x buffer holds the coarse solution
     vcycle<W>(ctx, H, lev + 1, C.b, xc, done, st);
-    launch_plain<W>(ctx, C.P, xc, x, 1.0, done, st);                                           // prolong + correct
+    launch_plain<W>(ctx, C.P, C.planP, xc, x, 1.0, done, st);                                           // prolong + correct
     chebyshev<W>(ctx, L, b, x, x, done, st);                                                   // post-smooth
 }
 
@@ -563,7 +571,7 @@ double estimate_lambda_max(mpet_ctx* ctx, AmgLevel& L, cudaStream_t st) {
     CUDA_CHECK(cudaMemcpy(x, x0.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     double lam = 0;
     for (int it = 0; it < 20; ++it) {
-        launch_plain<1>(ctx, L.A, x, y, 0.0, nullptr, st);
+        launch_plain<1>(ctx, L.A, SpmmPlan(), x, y, 0.0, nullptr, st);
         k_scale_by<<<grid_for(n, 256), 256, 0, st>>>(n, L.dinv, y);
         LAUNCH_CHECK(ctx);
         CUDA_CHECK(cudaMemcpyAsync(h.data(), y, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -619,10 +627,19 @@ void extend_by_aggregation(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
     }
 }
 
+void make_plan(mpet_ctx* ctx, const DevCsr& M, SpmmPlan& plan) {
+    if (M.nrows < 20000 || M.nnz == 0) return;      // small levels: launch latency dominates either way
+    std::vector<int32_t> rp(M.nrows + 1);
+    CUDA_CHECK(cudaMemcpy(rp.data(), M.rowptr, sizeof(int32_t) * (M.nrows + 1), cudaMemcpyDeviceToHost));
+    if (!staged_build_spmm_plan(ctx, rp, plan)) plan = SpmmPlan();
+}
+
 void finish_hierarchy(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
     for (auto& L : H.levels) {
         alloc_level_work(ctx, L, H.nrhs);
         L.lambda_max = estimate_lambda_max(ctx, L, st);
+        make_plan(ctx, L.A, L.planA);
+        if (L.P.nrows > 0) { make_plan(ctx, L.P, L.planP); make_plan(ctx, L.R, L.planR); }
     }
 }
 

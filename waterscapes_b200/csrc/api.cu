@@ -145,6 +145,8 @@ int mpet_set_mesh(mpet_ctx* ctx, const double* coords_dev, const int32_t* cells_
     build_space(ctx, st);
     compute_geometry(ctx, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+    staged_build_block_plans(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(st));
     MPET_CATCH(ctx)
 }
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 
 #include "../../include/mpet_b200.h"
+#include "staged.h"
 
 #define MPET_MAX_NETWORKS 8
 
@@ -64,6 +65,7 @@ struct AmgLevel {
     double* r = nullptr;
     double* t = nullptr;
     double lambda_max = 0.0;  // estimate of rho(D^-1 A)
+    SpmmPlan planA, planP, planR;   // staged-kernel chunk tables (nchunks == 0: not staged)
 };
 
 struct AmgHierarchy {
@@ -131,6 +133,8 @@ struct mpet_ctx {
     uint8_t* bc_mask_int = nullptr;   // [Nint] same in the solver-internal layout
     int32_t* bc_dofs_int = nullptr;   // [n_bc] internal indices of the Dirichlet dofs
     double* scratch_int[2] = {nullptr, nullptr};   // [Nint] layout-conversion buffers
+    BlockPlan plan_u, plan_p;         // chunk tables of the staged block SpMV
+    bool staged_ok = false;
 
     // Krylov
     int method = 0, pc = 2, maxit = 10000, restart = 30;
@@ -146,7 +150,8 @@ template <typename T>
 T* dev_alloc(mpet_ctx* ctx, int64_t n) {
     if (n <= 0) n = 1;
     void* p = nullptr;
-    CUDA_CHECK(cudaMalloc(&p, (size_t)n * sizeof(T)));
+    // 64 bytes of slack: the bulk-copy kernels read 16-byte aligned supersets of array slices
+    CUDA_CHECK(cudaMalloc(&p, (size_t)n * sizeof(T) + 64));
     (ctx->arena ? *ctx->arena : ctx->allocs).push_back(p);
     ctx->bytes += n * (int64_t)sizeof(T);
     return (T*)p;
@@ -194,6 +199,12 @@ void ensure_m22(mpet_ctx* ctx, cudaStream_t st);
 void amg_setup(mpet_ctx* ctx, cudaStream_t st);
 void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st);
 void amg_free(mpet_ctx* ctx);
+// staged.cu
+void staged_build_block_plans(mpet_ctx* ctx);
+bool staged_block_spmv(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done, cudaStream_t st);
+bool staged_build_spmm_plan(mpet_ctx* ctx, const std::vector<int32_t>& rp, SpmmPlan& plan);
+void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
+                 double* out, double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st);
 // spmv.cu
 void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
               const double* vals, const double* x, double* y, double beta, const uint8_t* rowmask,

@@ -316,6 +316,7 @@ void csr32_spmm(mpet_ctx* ctx, const DevCsr& M, const double* x, int64_t ldx, do
 
 void block_spmv(mpet_ctx* ctx, const double* x_int, double* y_int, const uint8_t* mask_int, const int* done,
                 cudaStream_t st) {
+    if (staged_block_spmv(ctx, x_int, y_int, mask_int, done, st)) return;
     switch (ctx->A) {
         case 0: launch_block<0>(ctx, x_int, y_int, mask_int, done, st); break;
         case 1: launch_block<1>(ctx, x_int, y_int, mask_int, done, st); break;

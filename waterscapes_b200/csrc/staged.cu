@@ -1,0 +1,501 @@
+// Shared-memory-staged sparse kernels: the matrix stream is moved by the bulk-async copy engine
+// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), warps only gather and reduce.
+//
+// Why (profiles/r01_*): the warp-per-row kernels are latency-bound.  Each warp walks a chain of
+// dependent DRAM round trips (row pointers -> values/indices -> gather -> epilogue operands) and
+// register pressure caps occupancy, so only ~1/3 of HBM bandwidth is reached.  Here a persistent CTA
+// owns a double-buffered ring of stages; one elected thread asks the copy engine for the next chunk
+// (a run of consecutive rows whose values, column indices and row pointers are CONTIGUOUS in memory),
+// while the eight warps consume the previous chunk out of shared memory.  The only long-latency
+// operation left in a warp is the 256-bit gather of the neighbour's vector entries.
+//
+// Two kernels share the machinery:
+//   k_block_rows_staged : the MPET block system, one "node" = NR rows that share their column
+//                         structure (3 displacement rows of a P2 node / A pressure rows of a vertex).
+//   k_spmm_staged       : scalar CSR matrix applied to W-wide vectors with the fused Chebyshev /
+//                         residual epilogue of the AMG V-cycle.
+#include "ctx.h"
+#include "layout.cuh"
+#include "staged.h"
+#include <algorithm>
+
+namespace {
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+constexpr int kStages = 2;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ------------------------------------------------------------------------------- block rows
+// shared-memory stage of k_block_rows_staged
+template <int NR>
+struct BlockStage {
+    double vals[NR][BLK_CAPV + 2];
+    int32_t colA[BLK_CAPA + 8];
+    int32_t colB[BLK_CAPB + 8];
+    int32_t rpA[BLK_NNMAX + 8];
+    int32_t rpB[BLK_NNMAX + 8];
+};
+
+struct GroupBase { int64_t v[MPET_MAX_NETWORKS]; };
+
+// NR rows per node, NA scalar (pressure) column blocks.  U_OUT: rows are the displacement of a P2 node
+// (output = one padded 256-bit store), else the pressures of a vertex (NR scalar stores, stride nv).
+template <int NR, int NA, bool U_OUT>
+__global__ void __launch_bounds__(kThreads)
+k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase gbase,
+                    const int32_t* __restrict__ rpA, const int32_t* __restrict__ colA,
+                    const int32_t* __restrict__ rpB, const int32_t* __restrict__ colB,
+                    const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                    int64_t n2, int64_t nv, const uint8_t* __restrict__ mask, const int* __restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BlockStage<NR>* stage = reinterpret_cast<BlockStage<NR>*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(BlockStage<NR>));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int ci, int s) {      // called by thread 0 only
+        const BlockChunk c = chunks[ci];
+        BlockStage<NR>& S = stage[s];
+        uint32_t total = 0;
+        // row-pointer slices (aligned to 4 ints)
+        const uint32_t rp_bytes = (uint32_t)c.rp_len * 4u;
+        total += 2 * rp_bytes;
+        // column indices
+        const uint32_t ca_bytes = (uint32_t)c.cA_len * 4u, cb_bytes = (uint32_t)c.cB_len * 4u;
+        total += ca_bytes + cb_bytes;
+        uint32_t vbytes[NR];
+        int64_t vstart[NR];
+#pragma unroll
+        for (int g = 0; g < NR; ++g) {
+            const int64_t s0 = gbase.v[g] + c.v_rel;
+            vstart[g] = s0 & ~(int64_t)1;
+            vbytes[g] = (uint32_t)((((s0 - vstart[g]) + c.v_len + 1) & ~(int64_t)1) * 8);
+            total += vbytes[g];
+        }
+        mbar_expect_tx(&full[s], total);
+        bulk_g2s(S.rpA, rpA + c.rp_off, rp_bytes, &full[s]);
+        bulk_g2s(S.rpB, rpB + c.rp_off, rp_bytes, &full[s]);
+        if (ca_bytes) bulk_g2s(S.colA, colA + c.cA_off, ca_bytes, &full[s]);
+        if (cb_bytes) bulk_g2s(S.colB, colB + c.cB_off, cb_bytes, &full[s]);
+#pragma unroll
+        for (int g = 0; g < NR; ++g) bulk_g2s(S.vals[g], vals + vstart[g], vbytes[g], &full[s]);
+    };
+
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages - 1; ++s)
+            if (first + s * stride < nchunks) issue(first + s * stride, s);
+    }
+    int it = 0;
+    for (int ci = first; ci < nchunks; ci += stride, ++it) {
+        const int s = it % kStages;
+        if (threadIdx.x == 0) {
+            const int nxt = ci + (kStages - 1) * stride;
+            if (nxt < nchunks) issue(nxt, (it + kStages - 1) % kStages);
+        }
+        mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+        const BlockChunk c = chunks[ci];
+        const BlockStage<NR>& S = stage[s];
+        const int rsk = c.n0 - c.rp_off;                    // skew of the row-pointer slices
+        const int32_t a_base = S.rpA[rsk], b_base = S.rpB[rsk];
+        const int ska = a_base - c.cA_off, skb = b_base - c.cB_off;
+        int vsk[NR];
+#pragma unroll
+        for (int g = 0; g < NR; ++g) vsk[g] = (int)((gbase.v[g] + c.v_rel) & 1);
+
+        for (int nl = warp; nl < c.nn; nl += kWarps) {
+            const int32_t ra = S.rpA[rsk + nl], rb = S.rpB[rsk + nl];
+            const int dA = S.rpA[rsk + nl + 1] - ra, dB = S.rpB[rsk + nl + 1] - rb;
+            const int eA = ra - a_base + ska, eB = rb - b_base + skb;
+            const int rel = 3 * (ra - a_base) + NA * (rb - b_base);
+            double acc[NR];
+#pragma unroll
+            for (int g = 0; g < NR; ++g) acc[g] = 0.0;
+            for (int j = lane; j < dA; j += 32) {
+                const int32_t col = S.colA[eA + j];
+                const d4 xv = ld256_gather(x + 4 * (int64_t)col);
+#pragma unroll
+                for (int g = 0; g < NR; ++g) {
+                    const double* v = S.vals[g] + vsk[g] + rel + j;
+                    acc[g] += v[0] * xv.x + v[dA] * xv.y + v[2 * dA] * xv.z;
+                }
+            }
+            if (NA > 0) {
+                const double* p = x + 4 * n2;
+                for (int j = lane; j < dB; j += 32) {
+                    const int32_t col = S.colB[eB + j];
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) {
+                        const double pv = __ldg(p + (int64_t)i * nv + col);
+#pragma unroll
+                        for (int g = 0; g < NR; ++g) acc[g] += S.vals[g][vsk[g] + rel + 3 * dA + i * dB + j] * pv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < NR; ++g) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o);
+            }
+            if (lane == 0) {
+                const int64_t node = (int64_t)c.n0 + nl;
+                if (U_OUT) {
+                    d4 out = {acc[0], NR > 1 ? acc[NR > 1 ? 1 : 0] : 0.0, NR > 2 ? acc[NR > 2 ? 2 : 0] : 0.0, 0.0};
+                    if (mask) {
+                        const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + 4 * node);
+                        if (m) {
+                            const d4 xa = ld256(x + 4 * node);
+                            if (m & 0x000000ffu) out.x = xa.x;
+                            if (m & 0x0000ff00u) out.y = xa.y;
+                            if (m & 0x00ff0000u) out.z = xa.z;
+                        }
+                    }
+                    st256(y + 4 * node, out);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < NR; ++g) {
+                        const int64_t idx = 4 * n2 + (int64_t)g * nv + node;
+                        y[idx] = (mask && mask[idx]) ? x[idx] : acc[g];
+                    }
+                }
+            }
+        }
+        __syncthreads();     // every warp is done with stage s before thread 0 refills it next iteration
+    }
+}
+
+// ------------------------------------------------------------------------------- scalar SpMM
+template <int W>
+struct SpmmStage {
+    double vals[SPM_CAP + 2];
+    int32_t cols[SPM_CAP + 8];
+    int32_t rp[SPM_ROWS + 8];
+};
+
+enum { SEPI_RESID = 0, SEPI_CHEB = 1, SEPI_PLAIN = 2 };
+
+// Row groups of LANES threads; epilogues as in amg.cu (RESID: out = b - Ax; CHEB: Chebyshev step;
+// PLAIN: out = Ax + beta*out).
+template <int W, int LANES, int EPI>
+__global__ void __launch_bounds__(kThreads)
+k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __restrict__ rowptr,
+              const int32_t* __restrict__ cols, const double* __restrict__ vals, const double* __restrict__ x,
+              const double* __restrict__ b, double* __restrict__ out, double* __restrict__ d,
+              const double* __restrict__ dinv, double c1, double c2, const int* __restrict__ done) {
+    if (done && *done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpmmStage<W>* stage = reinterpret_cast<SpmmStage<W>*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(SpmmStage<W>));
+    const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    constexpr int kGroups = kThreads / LANES;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int ci, int s) {
+        const SpmmChunk c = chunks[ci];
+        SpmmStage<W>& S = stage[s];
+        const uint32_t vb = (uint32_t)c.v_len * 8u, cb = (uint32_t)c.c_len * 4u, rb = (uint32_t)c.rp_len * 4u;
+        mbar_expect_tx(&full[s], vb + cb + rb);
+        bulk_g2s(S.rp, rowptr + c.rp_off, rb, &full[s]);
+        if (vb) bulk_g2s(S.vals, vals + c.v_off, vb, &full[s]);
+        if (cb) bulk_g2s(S.cols, cols + c.c_off, cb, &full[s]);
+    };
+
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages - 1; ++s)
+            if (first + s * stride < nchunks) issue(first + s * stride, s);
+    }
+    int it = 0;
+    for (int ci = first; ci < nchunks; ci += stride, ++it) {
+        const int s = it % kStages;
+        if (threadIdx.x == 0) {
+            const int nxt = ci + (kStages - 1) * stride;
+            if (nxt < nchunks) issue(nxt, (it + kStages - 1) % kStages);
+        }
+        const SpmmChunk c = chunks[ci];
+        mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+        const SpmmStage<W>& S = stage[s];
+        const int rsk = c.r0 - c.rp_off;
+        const int32_t e_base = S.rp[rsk];
+        const int vsk = e_base - c.v_off, csk = e_base - c.c_off;
+        for (int rl = group; rl < c.nrows; rl += kGroups) {
+            const int64_t row = (int64_t)c.r0 + rl;
+            const int32_t e0 = S.rp[rsk + rl] - e_base, e1 = S.rp[rsk + rl + 1] - e_base;
+            double eb1 = 0, ed1 = 0, ex1 = 0, edi = 0;
+            d4 eb4 = {0, 0, 0, 0}, ed4 = {0, 0, 0, 0}, ex4 = {0, 0, 0, 0};
+            if (lane == 0) {
+                if constexpr (W == 1) {
+                    if (EPI != SEPI_PLAIN) eb1 = b[row];
+                    if (EPI == SEPI_CHEB) { edi = dinv[row]; ex1 = x[row]; if (c1 != 0.0) ed1 = d[row]; }
+                    if (EPI == SEPI_PLAIN && c1 != 0.0) ex1 = out[row];
+                } else {
+                    if (EPI != SEPI_PLAIN) eb4 = ld256(b + 4 * row);
+                    if (EPI == SEPI_CHEB) { edi = dinv[row]; ex4 = ld256(x + 4 * row); if (c1 != 0.0) ed4 = ld256(d + 4 * row); }
+                    if (EPI == SEPI_PLAIN && c1 != 0.0) ex4 = ld256(out + 4 * row);
+                }
+            }
+            double a1 = 0.0;
+            d4 a4 = {0, 0, 0, 0};
+            for (int e = e0 + lane; e < e1; e += LANES) {
+                const double v = S.vals[vsk + e];
+                const int32_t col = S.cols[csk + e];
+                if constexpr (W == 1) {
+                    a1 += v * __ldg(x + col);
+                } else {
+                    const d4 g = ld256_gather(x + 4 * (int64_t)col);
+                    a4.x += v * g.x; a4.y += v * g.y; a4.z += v * g.z; a4.w += v * g.w;
+                }
+            }
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) {
+                if constexpr (W == 1) {
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o, LANES);
+                } else {
+                    a4.x += __shfl_xor_sync(0xffffffffu, a4.x, o, LANES);
+                    a4.y += __shfl_xor_sync(0xffffffffu, a4.y, o, LANES);
+                    a4.z += __shfl_xor_sync(0xffffffffu, a4.z, o, LANES);
+                    a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o, LANES);
+                }
+            }
+            if (lane == 0) {
+                if constexpr (W == 1) {
+                    if (EPI == SEPI_PLAIN) {
+                        out[row] = a1 + c1 * ex1;
+                    } else {
+                        const double res = eb1 - a1;
+                        if (EPI == SEPI_RESID) out[row] = res;
+                        else { const double dn = c2 * edi * res + c1 * ed1; d[row] = dn; out[row] = ex1 + dn; }
+                    }
+                } else {
+                    if (EPI == SEPI_PLAIN) {
+                        d4 o = {a4.x + c1 * ex4.x, a4.y + c1 * ex4.y, a4.z + c1 * ex4.z, a4.w + c1 * ex4.w};
+                        st256(out + 4 * row, o);
+                    } else {
+                        d4 res = {eb4.x - a4.x, eb4.y - a4.y, eb4.z - a4.z, eb4.w - a4.w};
+                        if (EPI == SEPI_RESID) {
+                            st256(out + 4 * row, res);
+                        } else {
+                            const double s2 = c2 * edi;
+                            d4 dn = {s2 * res.x + c1 * ed4.x, s2 * res.y + c1 * ed4.y, s2 * res.z + c1 * ed4.z,
+                                     s2 * res.w + c1 * ed4.w};
+                            st256(d + 4 * row, dn);
+                            d4 o = {ex4.x + dn.x, ex4.y + dn.y, ex4.z + dn.z, ex4.w + dn.w};
+                            st256(out + 4 * row, o);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+T* upload_vec(mpet_ctx* ctx, const std::vector<T>& h) {
+    T* d = dev_alloc<T>(ctx, (int64_t)h.size());
+    if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    return d;
+}
+
+template <int NR, int NA, bool U_OUT>
+void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
+                       const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
+                       cudaStream_t st) {
+    const size_t smem = kStages * sizeof(BlockStage<NR>) + kStages * sizeof(uint64_t);
+    auto kern = k_block_rows_staged<NR, NA, U_OUT>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int grid = std::min(P.nchunks, 2 * ctx->sm_count);
+    kern<<<grid, kThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x, y,
+                                       ctx->N2, ctx->Nv, mask, done);
+    LAUNCH_CHECK(ctx);
+}
+
+template <int NA>
+void block_rows_all(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done, cudaStream_t st) {
+    // value runs: row (k, a) starts at k*T + 3*rp22[a] + NA*rp21[a]; row (i, v) at 3*T + i*Tp + 3*rp12[v] + NA*rp11[v]
+    const int64_t T = 3 * ctx->g22.nnz + (int64_t)NA * ctx->g21.nnz;
+    const int64_t Tp = 3 * ctx->g12.nnz + (int64_t)NA * ctx->g11.nnz;
+    GroupBase gu, gp;
+    for (int k = 0; k < MPET_MAX_NETWORKS; ++k) { gu.v[k] = (int64_t)k * T; gp.v[k] = 3 * T + (int64_t)k * Tp; }
+    launch_block_rows<3, NA, true>(ctx, ctx->plan_u, gu, ctx->g22, ctx->g21, x, y, mask, done, st);
+    if (NA > 0)
+        launch_block_rows<(NA > 0 ? NA : 1), NA, false>(ctx, ctx->plan_p, gp, ctx->g12, ctx->g11, x, y, mask, done, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------- host: plans
+// Greedy chunking of consecutive nodes so that every staged array fits its shared-memory slot.
+static bool build_block_plan(mpet_ctx* ctx, const NodeGraph& gA, const NodeGraph& gB, int NA, int NR, BlockPlan& plan) {
+    const int64_t n = gA.nrows;
+    std::vector<int32_t> rpA(n + 1), rpB(n + 1);
+    CUDA_CHECK(cudaMemcpy(rpA.data(), gA.rowptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(rpB.data(), gB.rowptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    std::vector<BlockChunk> chunks;
+    int64_t a0 = 0;
+    while (a0 < n) {
+        int64_t a1 = a0;
+        const int rp_off = (int)(a0 & ~(int64_t)3);
+        while (a1 < n) {
+            const int64_t vlen = 3 * (int64_t)(rpA[a1 + 1] - rpA[a0]) + (int64_t)NA * (rpB[a1 + 1] - rpB[a0]);
+            const int64_t la = rpA[a1 + 1] - rpA[a0], lb = rpB[a1 + 1] - rpB[a0];
+            if (vlen > BLK_CAPV || la > BLK_CAPA || lb > BLK_CAPB || (a1 + 1 - rp_off) + 1 > BLK_NNMAX) break;
+            ++a1;
+        }
+        if (a1 == a0) return false;      // a single node does not fit: caller falls back
+        BlockChunk c;
+        c.n0 = (int32_t)a0;
+        c.nn = (int32_t)(a1 - a0);
+        c.rp_off = rp_off;
+        c.rp_len = (int32_t)((((a1 + 1) - rp_off) + 3) & ~(int64_t)3);
+        c.cA_off = rpA[a0] & ~3;
+        c.cA_len = ((rpA[a1] - c.cA_off) + 3) & ~3;
+        c.cB_off = rpB[a0] & ~3;
+        c.cB_len = ((rpB[a1] - c.cB_off) + 3) & ~3;
+        c.v_rel = 3 * (int64_t)rpA[a0] + (int64_t)NA * rpB[a0];
+        c.v_len = (int32_t)(3 * (int64_t)(rpA[a1] - rpA[a0]) + (int64_t)NA * (rpB[a1] - rpB[a0]));
+        c.pad = 0;
+        chunks.push_back(c);
+        a0 = a1;
+    }
+    (void)NR;
+    plan.nchunks = (int)chunks.size();
+    plan.chunks = upload_vec(ctx, chunks);
+    return true;
+}
+
+void staged_build_block_plans(mpet_ctx* ctx) {
+    ctx->staged_ok = build_block_plan(ctx, ctx->g22, ctx->g21, ctx->A, 3, ctx->plan_u);
+    if (ctx->staged_ok && ctx->A > 0)
+        ctx->staged_ok = build_block_plan(ctx, ctx->g12, ctx->g11, ctx->A, ctx->A, ctx->plan_p);
+}
+
+bool staged_block_spmv(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done,
+                       cudaStream_t st) {
+    if (!ctx->staged_ok) return false;
+    switch (ctx->A) {
+        case 0: block_rows_all<0>(ctx, x, y, mask, done, st); break;
+        case 1: block_rows_all<1>(ctx, x, y, mask, done, st); break;
+        case 2: block_rows_all<2>(ctx, x, y, mask, done, st); break;
+        case 3: block_rows_all<3>(ctx, x, y, mask, done, st); break;
+        case 4: block_rows_all<4>(ctx, x, y, mask, done, st); break;
+        default: return false;
+    }
+    return true;
+}
+
+// scalar CSR: chunks of consecutive rows with at most SPM_CAP entries / SPM_ROWS rows
+bool staged_build_spmm_plan(mpet_ctx* ctx, const std::vector<int32_t>& rp, SpmmPlan& plan) {
+    const int64_t n = (int64_t)rp.size() - 1;
+    std::vector<SpmmChunk> chunks;
+    int64_t r0 = 0;
+    while (r0 < n) {
+        const int rp_off = (int)(r0 & ~(int64_t)3);
+        int64_t r1 = r0;
+        while (r1 < n && (rp[r1 + 1] - rp[r0]) <= SPM_CAP && ((r1 + 1 - rp_off) + 1) <= SPM_ROWS) ++r1;
+        if (r1 == r0) return false;
+        SpmmChunk c;
+        c.r0 = (int32_t)r0;
+        c.nrows = (int32_t)(r1 - r0);
+        c.rp_off = rp_off;
+        c.rp_len = (int32_t)((((r1 + 1) - rp_off) + 3) & ~(int64_t)3);
+        c.v_off = rp[r0] & ~1;
+        c.v_len = ((rp[r1] - c.v_off) + 1) & ~1;
+        c.c_off = rp[r0] & ~3;
+        c.c_len = ((rp[r1] - c.c_off) + 3) & ~3;
+        chunks.push_back(c);
+        r0 = r1;
+    }
+    plan.nchunks = (int)chunks.size();
+    plan.chunks = upload_vec(ctx, chunks);
+    return true;
+}
+
+template <int W, int LANES, int EPI>
+static void launch_spmm_staged(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
+                               double* out, double* d, const double* dinv, double c1, double c2, const int* done,
+                               cudaStream_t st) {
+    const size_t smem = kStages * sizeof(SpmmStage<W>) + kStages * sizeof(uint64_t);
+    auto kern = k_spmm_staged<W, LANES, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int grid = std::min(P.nchunks, 4 * ctx->sm_count);
+    kern<<<grid, kThreads, smem, st>>>(P.chunks, P.nchunks, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
+    LAUNCH_CHECK(ctx);
+}
+
+template <int W, int EPI>
+static void spmm_staged_lanes(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
+                              double* out, double* d, const double* dinv, double c1, double c2, const int* done,
+                              cudaStream_t st) {
+    const double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
+    if (mean > 40) launch_spmm_staged<W, 32, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    else if (mean > 12) launch_spmm_staged<W, 16, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    else if (mean > 5) launch_spmm_staged<W, 8, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    else launch_spmm_staged<W, 4, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+}
+
+// epi: 0 = residual, 1 = Chebyshev step, 2 = plain (out = M x + c1 * out)
+void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
+                 double* out, double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
+    if (W == 4) {
+        if (epi == 0) spmm_staged_lanes<4, SEPI_RESID>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else if (epi == 1) spmm_staged_lanes<4, SEPI_CHEB>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else spmm_staged_lanes<4, SEPI_PLAIN>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    } else {
+        if (epi == 0) spmm_staged_lanes<1, SEPI_RESID>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else if (epi == 1) spmm_staged_lanes<1, SEPI_CHEB>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else spmm_staged_lanes<1, SEPI_PLAIN>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    }
+}
