@@ -628,7 +628,7 @@ void extend_by_aggregation(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
 }
 
 void make_plan(mpet_ctx* ctx, const DevCsr& M, SpmmPlan& plan) {
-    if (M.nrows < 20000 || M.nnz == 0) return;      // small levels: launch latency dominates either way
+    if (M.nrows < 4000 || M.nnz == 0) return;      // small levels: launch latency dominates either way
     std::vector<int32_t> rp(M.nrows + 1);
     CUDA_CHECK(cudaMemcpy(rp.data(), M.rowptr, sizeof(int32_t) * (M.nrows + 1), cudaMemcpyDeviceToHost));
     if (!staged_build_spmm_plan(ctx, rp, plan)) plan = SpmmPlan();

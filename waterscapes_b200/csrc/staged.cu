@@ -262,12 +262,16 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
         const int rsk = c.r0 - c.rp_off;
         const int32_t e_base = S.rp[rsk];
         const int vsk = e_base - c.v_off, csk = e_base - c.c_off;
-        for (int rl = group; rl < c.nrows; rl += kGroups) {
-            const int64_t row = (int64_t)c.r0 + rl;
-            const int32_t e0 = S.rp[rsk + rl] - e_base, e1 = S.rp[rsk + rl + 1] - e_base;
+        // warp-uniform trip count: every lane takes part in the shuffles even when its group has no row
+        for (int rbase = 0; rbase < c.nrows; rbase += kGroups) {
+            const int rl = rbase + group;
+            const bool active = rl < c.nrows;
+            const int64_t row = (int64_t)c.r0 + (active ? rl : 0);
+            const int32_t e0 = active ? S.rp[rsk + rl] - e_base : 0;
+            const int32_t e1 = active ? S.rp[rsk + rl + 1] - e_base : 0;
             double eb1 = 0, ed1 = 0, ex1 = 0, edi = 0;
             d4 eb4 = {0, 0, 0, 0}, ed4 = {0, 0, 0, 0}, ex4 = {0, 0, 0, 0};
-            if (lane == 0) {
+            if (lane == 0 && active) {
                 if constexpr (W == 1) {
                     if (EPI != SEPI_PLAIN) eb1 = b[row];
                     if (EPI == SEPI_CHEB) { edi = dinv[row]; ex1 = x[row]; if (c1 != 0.0) ed1 = d[row]; }
@@ -301,7 +305,7 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
                     a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o, LANES);
                 }
             }
-            if (lane == 0) {
+            if (lane == 0 && active) {
                 if constexpr (W == 1) {
                     if (EPI == SEPI_PLAIN) {
                         out[row] = a1 + c1 * ex1;
