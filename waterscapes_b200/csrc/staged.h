@@ -4,9 +4,9 @@
 #include <vector>
 
 // capacities of one shared-memory stage
-#define BLK_CAPV 1536     // values per row group
-#define BLK_CAPA 512      // primary (vector-valued) column indices
-#define BLK_CAPB 512      // secondary (scalar) column indices
+#define BLK_CAPV 1344     // values per row group
+#define BLK_CAPA 448      // primary (vector-valued) column indices
+#define BLK_CAPB 448      // secondary (scalar) column indices
 #define BLK_NNMAX 128     // nodes
 #define SPM_CAP 2048      // entries
 #define SPM_ROWS 256      // rows
