@@ -84,9 +84,6 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockStage<NR>* stage = reinterpret_cast<BlockStage<NR>*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(BlockStage<NR>));
-    // gathered neighbour data of the current chunk (single-buffered; filled between two block barriers)
-    d4* xs = reinterpret_cast<d4*>(smem_raw + kStages * sizeof(BlockStage<NR>) + 64);
-    double* ps = reinterpret_cast<double*>(xs + (BLK_CAPA + 8));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -145,32 +142,17 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
 #pragma unroll
         for (int g = 0; g < NR; ++g) vsk[g] = (int)((gbase.v[g] + c.v_rel) & 1);
 
-        // phase 1: every thread gathers (all loads independent -> maximal memory-level parallelism)
-        {
-            const int nA = S.rpA[rsk + c.nn] - a_base, nB = S.rpB[rsk + c.nn] - b_base;
-            for (int e = threadIdx.x; e < nA; e += kThreads)
-                xs[e] = ld256_gather(x + 4 * (int64_t)S.colA[ska + e]);
-            if (NA > 0) {
-                const double* p = x + 4 * n2;
-                for (int e = threadIdx.x; e < nB; e += kThreads) {
-                    const int32_t col = S.colB[skb + e];
-#pragma unroll
-                    for (int i = 0; i < NA; ++i) ps[i * (BLK_CAPB + 8) + e] = __ldg(p + (int64_t)i * nv + col);
-                }
-            }
-        }
-        __syncthreads();
-        // phase 2: one warp per node, all operands in shared memory
         for (int nl = warp; nl < c.nn; nl += kWarps) {
             const int32_t ra = S.rpA[rsk + nl], rb = S.rpB[rsk + nl];
             const int dA = S.rpA[rsk + nl + 1] - ra, dB = S.rpB[rsk + nl + 1] - rb;
-            const int eA = ra - a_base, eB = rb - b_base;
-            const int rel = 3 * eA + NA * eB;
+            const int eA = ra - a_base + ska, eB = rb - b_base + skb;
+            const int rel = 3 * (ra - a_base) + NA * (rb - b_base);
             double acc[NR];
 #pragma unroll
             for (int g = 0; g < NR; ++g) acc[g] = 0.0;
             for (int j = lane; j < dA; j += 32) {
-                const d4 xv = xs[eA + j];
+                const int32_t col = S.colA[eA + j];
+                const d4 xv = ld256_gather(x + 4 * (int64_t)col);
 #pragma unroll
                 for (int g = 0; g < NR; ++g) {
                     const double* v = S.vals[g] + vsk[g] + rel + j;
@@ -178,10 +160,12 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
                 }
             }
             if (NA > 0) {
+                const double* p = x + 4 * n2;
                 for (int j = lane; j < dB; j += 32) {
+                    const int32_t col = S.colB[eB + j];
 #pragma unroll
                     for (int i = 0; i < NA; ++i) {
-                        const double pv = ps[i * (BLK_CAPB + 8) + eB + j];
+                        const double pv = __ldg(p + (int64_t)i * nv + col);
 #pragma unroll
                         for (int g = 0; g < NR; ++g) acc[g] += S.vals[g][vsk[g] + rel + 3 * dA + i * dB + j] * pv;
                     }
@@ -365,8 +349,7 @@ template <int NR, int NA, bool U_OUT>
 void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
                        const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
                        cudaStream_t st) {
-    const size_t smem = kStages * sizeof(BlockStage<NR>) + 64 + (BLK_CAPA + 8) * sizeof(d4) +
-                        (size_t)(NA > 0 ? NA : 1) * (BLK_CAPB + 8) * sizeof(double);
+    const size_t smem = kStages * sizeof(BlockStage<NR>) + kStages * sizeof(uint64_t);
     auto kern = k_block_rows_staged<NR, NA, U_OUT>;
     static bool configured = false;
     if (!configured) {
