@@ -55,8 +55,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int kStages = 2;
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreads = 256;           // scalar SpMM
+constexpr int kBlkThreads = 512;        // block rows: 16 warps per CTA, 2 CTAs per SM
+constexpr int kWarps = kBlkThreads / 32;
 
 // ------------------------------------------------------------------------------- block rows
 // shared-memory stage of k_block_rows_staged
@@ -74,7 +75,7 @@ struct GroupBase { int64_t v[MPET_MAX_NETWORKS]; };
 // NR rows per node, NA scalar (pressure) column blocks.  U_OUT: rows are the displacement of a P2 node
 // (output = one padded 256-bit store), else the pressures of a vertex (NR scalar stores, stride nv).
 template <int NR, int NA, bool U_OUT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kBlkThreads, 2)
 k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase gbase,
                     const int32_t* __restrict__ rpA, const int32_t* __restrict__ colA,
                     const int32_t* __restrict__ rpB, const int32_t* __restrict__ colB,
@@ -84,6 +85,7 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockStage<NR>* stage = reinterpret_cast<BlockStage<NR>*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(BlockStage<NR>));
+    BlockChunk* desc = reinterpret_cast<BlockChunk*>(smem_raw + kStages * sizeof(BlockStage<NR>) + 64);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -94,6 +96,7 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
 
     auto issue = [&](int ci, int s) {      // called by thread 0 only
         const BlockChunk c = chunks[ci];
+        desc[s] = c;                        // consumers read the descriptor from shared memory (released by the arrive)
         BlockStage<NR>& S = stage[s];
         uint32_t total = 0;
         // row-pointer slices (aligned to 4 ints)
@@ -133,7 +136,7 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
             if (nxt < nchunks) issue(nxt, (it + kStages - 1) % kStages);
         }
         mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
-        const BlockChunk c = chunks[ci];
+        const BlockChunk c = desc[s];
         const BlockStage<NR>& S = stage[s];
         const int rsk = c.n0 - c.rp_off;                    // skew of the row-pointer slices
         const int32_t a_base = S.rpA[rsk], b_base = S.rpB[rsk];
@@ -147,27 +150,52 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
             const int dA = S.rpA[rsk + nl + 1] - ra, dB = S.rpB[rsk + nl + 1] - rb;
             const int eA = ra - a_base + ska, eB = rb - b_base + skb;
             const int rel = 3 * (ra - a_base) + NA * (rb - b_base);
+            const int64_t node = (int64_t)c.n0 + nl;
+            // every global load of the node's first sweep is issued before anything is consumed
+            uint32_t mword = 0;
+            if (U_OUT && mask && lane == 0) mword = __ldg(reinterpret_cast<const uint32_t*>(mask + 4 * node));
+            const bool hasA = lane < dA, hasB = (NA > 0) && lane < dB;
+            d4 xv = {0, 0, 0, 0};
+            if (hasA) xv = ld256_gather(x + 4 * (int64_t)S.colA[eA + lane]);
+            double pv[NA > 0 ? NA : 1];
+            const double* p = x + 4 * n2;
+            if (NA > 0) {
+                const int32_t colb = hasB ? S.colB[eB + lane] : 0;
+#pragma unroll
+                for (int i = 0; i < NA; ++i) pv[i] = hasB ? __ldg(p + (int64_t)i * nv + colb) : 0.0;
+            }
             double acc[NR];
 #pragma unroll
             for (int g = 0; g < NR; ++g) acc[g] = 0.0;
-            for (int j = lane; j < dA; j += 32) {
-                const int32_t col = S.colA[eA + j];
-                const d4 xv = ld256_gather(x + 4 * (int64_t)col);
+            if (hasA) {
 #pragma unroll
                 for (int g = 0; g < NR; ++g) {
-                    const double* v = S.vals[g] + vsk[g] + rel + j;
+                    const double* v = S.vals[g] + vsk[g] + rel + lane;
                     acc[g] += v[0] * xv.x + v[dA] * xv.y + v[2 * dA] * xv.z;
                 }
             }
+            if (NA > 0 && hasB) {
+#pragma unroll
+                for (int i = 0; i < NA; ++i)
+#pragma unroll
+                    for (int g = 0; g < NR; ++g) acc[g] += S.vals[g][vsk[g] + rel + 3 * dA + i * dB + lane] * pv[i];
+            }
+            for (int j = lane + 32; j < dA; j += 32) {            // nodes with more than 32 neighbours
+                const d4 xw = ld256_gather(x + 4 * (int64_t)S.colA[eA + j]);
+#pragma unroll
+                for (int g = 0; g < NR; ++g) {
+                    const double* v = S.vals[g] + vsk[g] + rel + j;
+                    acc[g] += v[0] * xw.x + v[dA] * xw.y + v[2 * dA] * xw.z;
+                }
+            }
             if (NA > 0) {
-                const double* p = x + 4 * n2;
-                for (int j = lane; j < dB; j += 32) {
+                for (int j = lane + 32; j < dB; j += 32) {
                     const int32_t col = S.colB[eB + j];
 #pragma unroll
                     for (int i = 0; i < NA; ++i) {
-                        const double pv = __ldg(p + (int64_t)i * nv + col);
+                        const double pw = __ldg(p + (int64_t)i * nv + col);
 #pragma unroll
-                        for (int g = 0; g < NR; ++g) acc[g] += S.vals[g][vsk[g] + rel + 3 * dA + i * dB + j] * pv;
+                        for (int g = 0; g < NR; ++g) acc[g] += S.vals[g][vsk[g] + rel + 3 * dA + i * dB + j] * pw;
                     }
                 }
             }
@@ -177,11 +205,10 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
                 for (int o = 16; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o);
             }
             if (lane == 0) {
-                const int64_t node = (int64_t)c.n0 + nl;
                 if (U_OUT) {
                     d4 out = {acc[0], NR > 1 ? acc[NR > 1 ? 1 : 0] : 0.0, NR > 2 ? acc[NR > 2 ? 2 : 0] : 0.0, 0.0};
                     if (mask) {
-                        const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + 4 * node);
+                        const uint32_t m = mword;
                         if (m) {
                             const d4 xa = ld256(x + 4 * node);
                             if (m & 0x000000ffu) out.x = xa.x;
@@ -349,7 +376,7 @@ template <int NR, int NA, bool U_OUT>
 void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
                        const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
                        cudaStream_t st) {
-    const size_t smem = kStages * sizeof(BlockStage<NR>) + kStages * sizeof(uint64_t);
+    const size_t smem = kStages * sizeof(BlockStage<NR>) + 64 + kStages * sizeof(BlockChunk);
     auto kern = k_block_rows_staged<NR, NA, U_OUT>;
     static bool configured = false;
     if (!configured) {
@@ -357,7 +384,7 @@ void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, c
         configured = true;
     }
     int grid = std::min(P.nchunks, 2 * ctx->sm_count);
-    kern<<<grid, kThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x, y,
+    kern<<<grid, kBlkThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x, y,
                                        ctx->N2, ctx->Nv, mask, done);
     LAUNCH_CHECK(ctx);
 }
