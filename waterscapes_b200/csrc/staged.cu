@@ -54,7 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr int kThreads = 256;           // scalar SpMM
 constexpr int kBlkThreads = 512;        // block rows: 16 warps per CTA, 2 CTAs per SM
 constexpr int kWarps = kBlkThreads / 32;
@@ -252,6 +252,7 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SpmmStage<W>* stage = reinterpret_cast<SpmmStage<W>*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(SpmmStage<W>));
+    SpmmChunk* desc = reinterpret_cast<SpmmChunk*>(smem_raw + kStages * sizeof(SpmmStage<W>) + 64);
     const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
     constexpr int kGroups = kThreads / LANES;
 
@@ -263,6 +264,7 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
 
     auto issue = [&](int ci, int s) {
         const SpmmChunk c = chunks[ci];
+        desc[s] = c;
         SpmmStage<W>& S = stage[s];
         const uint32_t vb = (uint32_t)c.v_len * 8u, cb = (uint32_t)c.c_len * 4u, rb = (uint32_t)c.rp_len * 4u;
         mbar_expect_tx(&full[s], vb + cb + rb);
@@ -283,8 +285,8 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
             const int nxt = ci + (kStages - 1) * stride;
             if (nxt < nchunks) issue(nxt, (it + kStages - 1) % kStages);
         }
-        const SpmmChunk c = chunks[ci];
         mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+        const SpmmChunk c = desc[s];
         const SpmmStage<W>& S = stage[s];
         const int rsk = c.r0 - c.rp_off;
         const int32_t e_base = S.rp[rsk];
@@ -494,7 +496,7 @@ template <int W, int LANES, int EPI>
 static void launch_spmm_staged(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
                                double* out, double* d, const double* dinv, double c1, double c2, const int* done,
                                cudaStream_t st) {
-    const size_t smem = kStages * sizeof(SpmmStage<W>) + kStages * sizeof(uint64_t);
+    const size_t smem = kStages * sizeof(SpmmStage<W>) + 64 + kStages * sizeof(SpmmChunk);
     auto kern = k_spmm_staged<W, LANES, EPI>;
     static bool configured = false;
     if (!configured) {
