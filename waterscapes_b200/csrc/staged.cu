@@ -54,7 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-constexpr int kStages = 3;
+constexpr int kStages = 2;     // measured: 3 stages of smaller chunks are slower (per-chunk barrier cost)
 constexpr int kThreads = 256;           // scalar SpMM
 constexpr int kBlkThreads = 512;        // block rows: 16 warps per CTA, 2 CTAs per SM
 constexpr int kWarps = kBlkThreads / 32;

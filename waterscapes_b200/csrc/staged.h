@@ -4,11 +4,11 @@
 #include <vector>
 
 // capacities of one shared-memory stage
-#define BLK_CAPV 896     // values per row group
-#define BLK_CAPA 300      // primary (vector-valued) column indices
-#define BLK_CAPB 300      // secondary (scalar) column indices
+#define BLK_CAPV 1344     // values per row group
+#define BLK_CAPA 448      // primary (vector-valued) column indices
+#define BLK_CAPB 448      // secondary (scalar) column indices
 #define BLK_NNMAX 128     // nodes
-#define SPM_CAP 1536      // entries
+#define SPM_CAP 2048      // entries
 #define SPM_ROWS 256      // rows
 
 struct BlockChunk {       // a run of consecutive nodes of the block system
