@@ -126,12 +126,24 @@ int mpet_solve(mpet_ctx* ctx, const double* b_dev, double* x_dev, double* info_h
 /* apply the preconditioner once: z = M^-1 r (tests) */
 int mpet_pc_apply(mpet_ctx* ctx, const double* r_dev, double* z_dev, void* stream);
 
-/* ---- multi-GPU (one process per GPU; rows owned by rank, ghost columns exchanged over NVLink) ---
- * nccl_uid_host: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host plumbing. */
+/* ---- multi-GPU (one process per GPU; rows owned by rank, ghost entries exchanged over NVLink) ---
+ * Replaces what DOLFIN + PETSc do under mpirun (src/mpet/utils/jobscript.sh:43): VecScatter halo
+ * updates inside MatMult and MPI_Allreduce in the Krylov dot products.  Every rank calls mpet_set_mesh
+ * with its OWN cells plus a one-cell ghost layer (no assembly collective is needed), then
+ *   mpet_nccl_unique_id : rank 0 creates the 128-byte ncclUniqueId; the host plumbing broadcasts it
+ *   mpet_attach_comm    : ncclCommInitRank on this context's device
+ *   mpet_set_halo       : neighbour ranks (host, ascending) and, per neighbour q, the LOCAL dof ids
+ *                         (numbering of this header) this rank sends to q / receives from q, as two
+ *                         concatenated device arrays with host offsets [n_neighbours+1]; both sides list
+ *                         a shared dof in the same order.  owned_dev u8[N]: 1 where this rank owns the dof.
+ * After that mpet_solve (MINRES) exchanges halos after every SpMV / preconditioner application, counts
+ * each dof once in the dot products and all-reduces them; the per-rank V-cycles are combined as an
+ * additive Schwarz preconditioner. */
+int mpet_nccl_unique_id(void* out128_host);
 int mpet_attach_comm(mpet_ctx* ctx, const void* nccl_uid_host, int rank, int nranks);
-/* owned/ghost layout of this rank's dofs, see DESIGN.md "Multi-GPU" */
-int mpet_set_partition(mpet_ctx* ctx, const int32_t* owner_of_local_dof_dev, int64_t n_owned,
-                       void* stream);
+int mpet_set_halo(mpet_ctx* ctx, int n_neighbours, const int* ranks_host, const int64_t* send_off_host,
+                  const int32_t* send_dofs_dev, const int64_t* recv_off_host, const int32_t* recv_dofs_dev,
+                  const uint8_t* owned_dev, void* stream);
 
 /* ---- instrumentation ---------------------------------------------------------------------------
  * number of kernels this library launched since the last reset (bench.py's "gpu_launches") */

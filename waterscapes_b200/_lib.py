@@ -45,7 +45,8 @@ PROTOTYPES = {
     "mpet_solve": (_int, [_c_ctx, _p, _p, C.POINTER(_f64), _p]),
     "mpet_pc_apply": (_int, [_c_ctx, _p, _p, _p]),
     "mpet_attach_comm": (_int, [_c_ctx, _p, _int, _int]),
-    "mpet_set_partition": (_int, [_c_ctx, _p, _i64, _p]),
+    "mpet_nccl_unique_id": (_int, [_p]),
+    "mpet_set_halo": (_int, [_c_ctx, _int, C.POINTER(_int), C.POINTER(_i64), _p, C.POINTER(_i64), _p, _p, _p]),
     "mpet_launch_count": (_i64, [_c_ctx, _int]),
     "mpet_profile": (_int, [_c_ctx, _int, C.POINTER(_f64)]),
     "mpet_device_bytes": (_i64, [_c_ctx]),

@@ -18,6 +18,9 @@ void amg_free(mpet_ctx* ctx);
 // dist.cu
 void dist_attach(mpet_ctx* ctx, const void* uid, int rank, int nranks);
 void dist_free(mpet_ctx* ctx);
+void dist_unique_id(void* out128);
+void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* send_off, const int32_t* send_idx_dev,
+                   const int64_t* recv_off, const int32_t* recv_idx_dev, const uint8_t* owned_dev, cudaStream_t st);
 
 namespace {
 __global__ void k_cell_dofs(const int32_t* __restrict__ cell_nodes, int64_t nc, int64_t n2, int64_t nv,
@@ -347,10 +350,21 @@ int mpet_attach_comm(mpet_ctx* ctx, const void* uid, int rank, int nranks) {
     MPET_CATCH(ctx)
 }
 
-int mpet_set_partition(mpet_ctx* ctx, const int32_t* owner, int64_t n_owned, void* stream) {
+int mpet_nccl_unique_id(void* out128_host) {
+    try {
+        dist_unique_id(out128_host);
+    } catch (const std::exception&) {
+        return -1;
+    }
+    return 0;
+}
+
+int mpet_set_halo(mpet_ctx* ctx, int n_neighbours, const int* ranks_host, const int64_t* send_off_host,
+                  const int32_t* send_dofs_dev, const int64_t* recv_off_host, const int32_t* recv_dofs_dev,
+                  const uint8_t* owned_dev, void* stream) {
     MPET_TRY(ctx)
-    (void)owner; (void)n_owned; (void)stream;
-    MPET_REQUIRE(false, "mpet_set_partition: not implemented yet");
+    dist_set_halo(ctx, n_neighbours, ranks_host, send_off_host, send_dofs_dev, recv_off_host, recv_dofs_dev,
+                  owned_dev, as_stream(stream));
     MPET_CATCH(ctx)
 }
 

@@ -140,6 +140,7 @@ struct mpet_ctx {
     int method = 0, pc = 2, maxit = 10000, restart = 30;
     double rtol = 1e-5, atol = 1e-50;
     struct KrylovWork* kw = nullptr;
+    struct DistState* dist = nullptr;           // NCCL communicator + halo plan (dist.cu)
     AmgHierarchy* amg_u = nullptr;              // scalar P2 block, 3 right-hand sides
     AmgHierarchy* amg_p[MPET_MAX_NETWORKS] = {};  // one per network
     double* jac_dinv = nullptr;                 // Jacobi preconditioner (pc = 1)

@@ -1,0 +1,197 @@
+// Multi-GPU: one process per GPU, mesh partitioned by cells with owned / ghost dofs.
+//
+// Replaces what DOLFIN + PETSc do under `mpirun` (utils/jobscript.sh:43): VecScatter halo updates in
+// MatMult and MPI_Allreduce in the Krylov dot products.  Here every rank holds its own cells plus a
+// one-cell ghost layer, so its OWNED rows are complete without any assembly collective; vectors carry
+// owned + ghost entries.  Two collectives remain, both over NCCL (NVLink 5 / NVSwitch):
+//   * halo exchange: pack owned boundary values -> ncclSend/ncclRecv inside one group -> unpack into
+//     the ghost entries (forward), or ghost contributions added into the owner (reverse, used by the
+//     additive-Schwarz application of the per-rank V-cycles);
+//   * all-reduce of the 1-3 Krylov scalars per iteration (in place on the device scalar).
+// NCCL is resolved at run time from the library already loaded in the process (torch's bundled
+// libnccl.so.2), so libmpet_b200.so has no link-time dependency on it.
+#include "ctx.h"
+#include "layout.cuh"
+#include <dlfcn.h>
+#include <cstring>
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+void load_nccl() {
+    if (g_nccl.handle) return;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) throw MpetError("NCCL (libnccl.so.2) is not loadable in this process");
+#define RESOLVE(field, sym)                                                        \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.handle, sym);                            \
+    if (!g_nccl.field) throw MpetError("NCCL symbol " sym " not found");
+    RESOLVE(GetUniqueId, "ncclGetUniqueId")
+    RESOLVE(CommInitRank, "ncclCommInitRank")
+    RESOLVE(CommDestroy, "ncclCommDestroy")
+    RESOLVE(GroupStart, "ncclGroupStart")
+    RESOLVE(GroupEnd, "ncclGroupEnd")
+    RESOLVE(Send, "ncclSend")
+    RESOLVE(Recv, "ncclRecv")
+    RESOLVE(AllReduce, "ncclAllReduce")
+    RESOLVE(GetErrorString, "ncclGetErrorString")
+#undef RESOLVE
+}
+
+#define NCCL_CHECK(call)                                                                     \
+    do {                                                                                     \
+        ncclResult_t r__ = (call);                                                           \
+        if (r__ != 0) {                                                                      \
+            char buf__[256];                                                                 \
+            snprintf(buf__, sizeof buf__, "%s:%d: NCCL: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r__)); \
+            throw MpetError(buf__);                                                          \
+        }                                                                                    \
+    } while (0)
+
+__global__ void k_pack(const int32_t* __restrict__ idx, int64_t n, const double* __restrict__ v,
+                       double* __restrict__ buf, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = v[idx[i]];
+}
+
+__global__ void k_unpack(const int32_t* __restrict__ idx, int64_t n, const double* __restrict__ buf,
+                         double* __restrict__ v, int add, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (add) v[idx[i]] += buf[i];   // indices of one message are unique, messages are applied in rank order
+    else v[idx[i]] = buf[i];
+}
+
+__global__ void k_api_to_internal_idx(const int32_t* __restrict__ in, int64_t n, int64_t n2, int32_t* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)api_to_internal(in[i], n2);
+}
+
+__global__ void k_own_internal(const uint8_t* __restrict__ own_api, int64_t n, int64_t n2, uint8_t* __restrict__ own_int) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) own_int[api_to_internal(i, n2)] = own_api[i];
+}
+
+}  // namespace
+
+struct DistState {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    std::vector<int> nbr;                 // neighbour ranks (ascending)
+    std::vector<int64_t> send_off, recv_off;   // [nnbr+1]
+    int32_t* send_idx = nullptr;          // internal-layout indices of owned dofs a neighbour needs
+    int32_t* recv_idx = nullptr;          // internal-layout indices of my ghost dofs
+    double* send_buf = nullptr;
+    double* recv_buf = nullptr;
+    uint8_t* own = nullptr;               // [Nint] 1 on owned dofs (pad lanes 0)
+};
+
+void dist_unique_id(void* out128) {
+    load_nccl();
+    ncclUniqueId id;
+    NCCL_CHECK(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+}
+
+void dist_attach(mpet_ctx* ctx, const void* uid, int rank, int nranks) {
+    load_nccl();
+    MPET_REQUIRE(ctx->dist == nullptr, "communicator already attached");
+    DistState* d = new DistState();
+    d->rank = rank;
+    d->nranks = nranks;
+    ncclUniqueId id;
+    memcpy(&id, uid, 128);
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    NCCL_CHECK(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
+    ctx->dist = d;
+}
+
+void dist_free(mpet_ctx* ctx) {
+    if (!ctx->dist) return;
+    if (ctx->dist->comm) g_nccl.CommDestroy(ctx->dist->comm);
+    delete ctx->dist;
+    ctx->dist = nullptr;
+}
+
+// dof indices arrive in the API (UFC) numbering of the LOCAL mesh
+void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* send_off, const int32_t* send_idx_dev,
+                   const int64_t* recv_off, const int32_t* recv_idx_dev, const uint8_t* owned_dev, cudaStream_t st) {
+    MPET_REQUIRE(ctx->dist != nullptr, "mpet_attach_comm must be called first");
+    MPET_REQUIRE(ctx->N > 0, "mpet_set_mesh must be called first");
+    DistState* d = ctx->dist;
+    d->nbr.assign(ranks, ranks + nnbr);
+    d->send_off.assign(send_off, send_off + nnbr + 1);
+    d->recv_off.assign(recv_off, recv_off + nnbr + 1);
+    const int64_t ns = d->send_off[nnbr], nr = d->recv_off[nnbr];
+    d->send_idx = dev_alloc<int32_t>(ctx, ns);
+    d->recv_idx = dev_alloc<int32_t>(ctx, nr);
+    d->send_buf = dev_alloc<double>(ctx, std::max<int64_t>(ns, nr));
+    d->recv_buf = dev_alloc<double>(ctx, std::max<int64_t>(ns, nr));
+    d->own = dev_alloc<uint8_t>(ctx, ctx->Nint);
+    if (ns) { k_api_to_internal_idx<<<grid_for(ns, 256), 256, 0, st>>>(send_idx_dev, ns, ctx->N2, d->send_idx); LAUNCH_CHECK(ctx); }
+    if (nr) { k_api_to_internal_idx<<<grid_for(nr, 256), 256, 0, st>>>(recv_idx_dev, nr, ctx->N2, d->recv_idx); LAUNCH_CHECK(ctx); }
+    CUDA_CHECK(cudaMemsetAsync(d->own, 0, ctx->Nint, st));
+    k_own_internal<<<grid_for(ctx->N, 256), 256, 0, st>>>(owned_dev, ctx->N, ctx->N2, d->own);
+    LAUNCH_CHECK(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+bool dist_active(mpet_ctx* ctx) { return ctx->dist != nullptr && ctx->dist->nranks > 1; }
+const uint8_t* dist_owned_mask(mpet_ctx* ctx) { return dist_active(ctx) ? ctx->dist->own : nullptr; }
+
+// forward: owners -> ghosts (copy).  reverse: ghosts -> owners (add).
+void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st) {
+    if (!dist_active(ctx)) return;
+    DistState* d = ctx->dist;
+    const int nn = (int)d->nbr.size();
+    const int32_t* pack_idx = reverse ? d->recv_idx : d->send_idx;
+    const int32_t* unpack_idx = reverse ? d->send_idx : d->recv_idx;
+    const std::vector<int64_t>& poff = reverse ? d->recv_off : d->send_off;
+    const std::vector<int64_t>& uoff = reverse ? d->send_off : d->recv_off;
+    const int64_t np = poff[nn], nu = uoff[nn];
+    if (np) { k_pack<<<grid_for(np, 256), 256, 0, st>>>(pack_idx, np, v, d->send_buf, done); LAUNCH_CHECK(ctx); }
+    NCCL_CHECK(g_nccl.GroupStart());
+    for (int q = 0; q < nn; ++q) {
+        const int64_t cs = poff[q + 1] - poff[q], cr = uoff[q + 1] - uoff[q];
+        if (cs) NCCL_CHECK(g_nccl.Send(d->send_buf + poff[q], (size_t)cs, NCCL_FLOAT64, d->nbr[q], d->comm, st));
+        if (cr) NCCL_CHECK(g_nccl.Recv(d->recv_buf + uoff[q], (size_t)cr, NCCL_FLOAT64, d->nbr[q], d->comm, st));
+    }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    if (reverse) {
+        // one kernel per neighbour, in rank order: a dof ghosted by two neighbours is summed deterministically
+        for (int q = 0; q < nn; ++q) {
+            const int64_t cr = uoff[q + 1] - uoff[q];
+            if (cr) { k_unpack<<<grid_for(cr, 256), 256, 0, st>>>(unpack_idx + uoff[q], cr, d->recv_buf + uoff[q], v, 1, done); LAUNCH_CHECK(ctx); }
+        }
+    } else if (nu) {
+        k_unpack<<<grid_for(nu, 256), 256, 0, st>>>(unpack_idx, nu, d->recv_buf, v, 0, done);
+        LAUNCH_CHECK(ctx);
+    }
+}
+
+void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st) {
+    if (!dist_active(ctx)) return;
+    NCCL_CHECK(g_nccl.AllReduce(dev_scalars, dev_scalars, (size_t)count, NCCL_FLOAT64, NCCL_SUM, ctx->dist->comm, st));
+}

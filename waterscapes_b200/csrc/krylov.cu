@@ -19,6 +19,12 @@
 #include <vector>
 
 void scatter_bc_values_int(mpet_ctx* ctx, double* out_int, cudaStream_t st);   // rhs.cu
+// multi-GPU hooks (dist.cu)
+bool dist_active(mpet_ctx* ctx);
+const uint8_t* dist_owned_mask(mpet_ctx* ctx);
+void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st);
+void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
+
 
 namespace {
 
@@ -49,12 +55,12 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
 
 __global__ void __launch_bounds__(kRedThreads)
 k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
-              double* __restrict__ partials, const int* __restrict__ done) {
+              double* __restrict__ partials, const uint8_t* __restrict__ own, const int* __restrict__ done) {
     if (done && *done) return;
     __shared__ double sm[32];
     double s = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        s += a[i] * b[i];
+        if (!own || own[i]) s += a[i] * b[i];      // multi-GPU: every dof is counted by its owner only
     s = block_reduce_sum(s, sm);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
@@ -67,7 +73,9 @@ __device__ double final_sum(const double* __restrict__ partials, int nparts, dou
 }
 
 __global__ void __launch_bounds__(kRedThreads)
-k_final_store(const double* __restrict__ partials, int nparts, double* __restrict__ out) {
+k_final_store(const double* __restrict__ partials, int nparts, double* __restrict__ out,
+              const int* __restrict__ done) {
+    if (done && *done) return;
     __shared__ double sm[32];
     double s = final_sum(partials, nparts, sm);
     if (threadIdx.x == 0) *out = s;
@@ -104,11 +112,10 @@ __global__ void k_abs_diag_inv(int64_t n, const int64_t* __restrict__ rowptr, co
 
 // ---------------------------------------------------------------------------------- MINRES
 __global__ void __launch_bounds__(kRedThreads)
-k_minres_init(const double* __restrict__ partials, int nparts, double rtol, double atol, int maxit,
+k_minres_init(const double* __restrict__ red, double rtol, double atol, int maxit,
               double* __restrict__ sc, int* __restrict__ fl) {
-    __shared__ double sm[32];
-    double dp = final_sum(partials, nparts, sm);
     if (threadIdx.x != 0) return;
+    double dp = *red;
     for (int i = 0; i < S_COUNT; ++i) sc[i] = 0.0;
     for (int i = 0; i < F_COUNT; ++i) fl[i] = 0;
     fl[F_MAXIT] = maxit;
@@ -133,12 +140,9 @@ __global__ void k_minres_start(int64_t n, const double* __restrict__ sc, const d
 }
 
 __global__ void __launch_bounds__(kRedThreads)
-k_minres_alpha(const double* __restrict__ partials, int nparts, double* __restrict__ sc,
-               const int* __restrict__ fl) {
+k_minres_alpha(const double* __restrict__ red, double* __restrict__ sc, const int* __restrict__ fl) {
     if (fl[F_DONE]) return;
-    __shared__ double sm[32];
-    double a = final_sum(partials, nparts, sm);
-    if (threadIdx.x == 0) sc[S_ALPHA] = a;
+    if (threadIdx.x == 0) sc[S_ALPHA] = *red;
 }
 
 // r -= alpha v + beta v_old ; z -= alpha u + beta u_old ; partial(r.z)
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(kRedThreads)
 k_minres_update(int64_t n, const double* __restrict__ sc, const double* __restrict__ v,
                 const double* __restrict__ v_old, const double* __restrict__ u,
                 const double* __restrict__ u_old, double* __restrict__ r, double* __restrict__ z,
-                double* __restrict__ partials, const int* __restrict__ done) {
+                double* __restrict__ partials, const uint8_t* __restrict__ own, const int* __restrict__ done) {
     if (*done) return;
     __shared__ double sm[32];
     const double alpha = sc[S_ALPHA], beta = sc[S_BETA];
@@ -155,18 +159,17 @@ k_minres_update(int64_t n, const double* __restrict__ sc, const double* __restri
         double ri = r[i] - alpha * v[i] - beta * v_old[i];
         double zi = z[i] - alpha * u[i] - beta * u_old[i];
         r[i] = ri; z[i] = zi;
-        s += ri * zi;
+        if (!own || own[i]) s += ri * zi;
     }
     s = block_reduce_sum(s, sm);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
 __global__ void __launch_bounds__(kRedThreads)
-k_minres_rotate(const double* __restrict__ partials, int nparts, double* __restrict__ sc, int* __restrict__ fl) {
+k_minres_rotate(const double* __restrict__ red, double* __restrict__ sc, int* __restrict__ fl) {
     if (fl[F_DONE]) return;
-    __shared__ double sm[32];
-    double dp = final_sum(partials, nparts, sm);
     if (threadIdx.x != 0) return;
+    double dp = *red;
     if (dp < 0.0) {
         // tolerate round-off-sized negatives (exact convergence), flag real indefiniteness
         if (-dp > 1e-12 * sc[S_NORM0] * sc[S_NORM0]) fl[F_BREAKDOWN] = 1;
@@ -268,7 +271,7 @@ __global__ void k_scale_copy(const double* __restrict__ src, double scale, int64
 struct KrylovWork {
     int64_t n = 0;
     double *r = nullptr, *z = nullptr, *v = nullptr, *v_old = nullptr, *u = nullptr, *u_old = nullptr,
-           *w1 = nullptr, *w2 = nullptr, *xi = nullptr, *bi = nullptr, *partials = nullptr, *sc = nullptr;
+           *w1 = nullptr, *w2 = nullptr, *xi = nullptr, *bi = nullptr, *partials = nullptr, *sc = nullptr, *red = nullptr;
     int* fl = nullptr;
     double* basis = nullptr;   // GMRES: (restart + 1) vectors
     int basis_m = 0;
@@ -286,6 +289,7 @@ static KrylovWork* get_work(mpet_ctx* ctx) {
     for (auto p : vecs) *p = dev_alloc<double>(ctx, ctx->Nint);
     k->partials = dev_alloc<double>(ctx, (int64_t)kRedBlocks * 8);
     k->sc = dev_alloc<double>(ctx, S_COUNT);
+    k->red = dev_alloc<double>(ctx, 8);
     k->fl = dev_alloc<int>(ctx, F_COUNT);
     k->hdev = dev_alloc<double>(ctx, 256);
     CUDA_CHECK(cudaMallocHost(&k->h_sc, sizeof(double) * S_COUNT));
@@ -333,6 +337,14 @@ static void pc_apply_flag(mpet_ctx* ctx, const double* r, double* z, const int* 
     }
 }
 
+static void pc_apply_dist(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
+    pc_apply_flag(ctx, r, z, done, st);
+    if (dist_active(ctx)) {
+        dist_halo(ctx, z, true, done, st);
+        dist_halo(ctx, z, false, done, st);
+    }
+}
+
 static void ensure_scratch(mpet_ctx* ctx) {
     for (int i = 0; i < 2; ++i)
         if (!ctx->scratch_int[i]) ctx->scratch_int[i] = dev_alloc<double>(ctx, ctx->Nint);
@@ -353,17 +365,35 @@ void spmv_api(mpet_ctx* ctx, const double* x, double* y, cudaStream_t st) {
     to_api(ctx, ctx->scratch_int[1], y, st);
 }
 
-static void dot_to(mpet_ctx* ctx, KrylovWork* k, const double* a, const double* b, const int* done, cudaStream_t st) {
-    k_dot_partial<<<kRedBlocks, kRedThreads, 0, st>>>(a, b, k->n, k->partials, done);
+
+// partials -> k->red[0] (fixed order), then the NCCL all-reduce over ranks when a communicator is attached
+static void finish_reduction(mpet_ctx* ctx, KrylovWork* k, const int* done, cudaStream_t st) {
+    k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->red, done);
     LAUNCH_CHECK(ctx);
+    dist_allreduce_sum(ctx, k->red, 1, st);
 }
+
+static void dot_to(mpet_ctx* ctx, KrylovWork* k, const double* a, const double* b, const int* done, cudaStream_t st) {
+    k_dot_partial<<<kRedBlocks, kRedThreads, 0, st>>>(a, b, k->n, k->partials, dist_owned_mask(ctx), done);
+    LAUNCH_CHECK(ctx);
+    finish_reduction(ctx, k, done, st);
+}
+
+// z = M^-1 r.  Multi-GPU: additive Schwarz over the overlapping per-rank blocks -- every rank applies its
+// local V-cycles, ghost contributions are ADDED into the owners (reverse halo), owners are copied back
+// to the ghosts (forward halo).  Symmetric and positive definite, as MINRES needs.
+static void pc_apply_dist(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st);
+
 
 // xi (internal layout) carries the Dirichlet values; r = b - A x on free rows, 0 on Dirichlet rows
 static void initial_residual(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
     if (ctx->n_bc > 0) scatter_bc_values_int(ctx, k->xi, st);
+    dist_halo(ctx, k->xi, false, nullptr, st);      // ghosts of x and b come from their owners
+    dist_halo(ctx, k->bi, false, nullptr, st);
     block_spmv(ctx, k->xi, k->v, nullptr, nullptr, st);
     k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr, k->n, k->r);
     LAUNCH_CHECK(ctx);
+    dist_halo(ctx, k->r, false, nullptr, st);       // ghost rows of the local matrix are incomplete
 }
 
 static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
@@ -373,9 +403,9 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     to_internal(ctx, b, k->bi, st);
     to_internal(ctx, x, k->xi, st);
     initial_residual(ctx, k, st);
-    pc_apply_flag(ctx, k->r, k->z, nullptr, st);
+    pc_apply_dist(ctx, k->r, k->z, nullptr, st);
     dot_to(ctx, k, k->r, k->z, nullptr, st);
-    k_minres_init<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, ctx->rtol, ctx->atol, ctx->maxit, k->sc, k->fl);
+    k_minres_init<<<1, 32, 0, st>>>(k->red, ctx->rtol, ctx->atol, ctx->maxit, k->sc, k->fl);
     LAUNCH_CHECK(ctx);
     const int* done = k->fl + F_DONE;
     k_minres_start<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->r, k->z, k->v, k->u, k->v_old, k->u_old, k->w1,
@@ -388,16 +418,18 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
             cudaEvent_t pe = prof_begin(ctx, st);
             block_spmv(ctx, k->u, k->r, mask, done, st);
             prof_end(ctx, PROF_SPMV, pe, st);
+            dist_halo(ctx, k->r, false, done, st);
             dot_to(ctx, k, k->r, k->u, done, st);
-            k_minres_alpha<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
+            k_minres_alpha<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
             LAUNCH_CHECK(ctx);
             pe = prof_begin(ctx, st);
-            pc_apply_flag(ctx, k->r, k->z, done, st);
+            pc_apply_dist(ctx, k->r, k->z, done, st);
             prof_end(ctx, PROF_PC, pe, st);
             k_minres_update<<<kRedBlocks, kRedThreads, 0, st>>>(n, k->sc, k->v, k->v_old, k->u, k->u_old, k->r,
-                                                                k->z, k->partials, done);
+                                                                k->z, k->partials, dist_owned_mask(ctx), done);
             LAUNCH_CHECK(ctx);
-            k_minres_rotate<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->sc, k->fl);
+            finish_reduction(ctx, k, done, st);
+            k_minres_rotate<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
             LAUNCH_CHECK(ctx);
             k_minres_finalize<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->xi, k->w1, k->w2, k->v, k->v_old, k->u,
                                                                 k->u_old, k->r, k->z, done);
@@ -440,6 +472,7 @@ static void multidot(mpet_ctx* ctx, KrylovWork* k, const double* V, int64_t ldv,
 }
 
 static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
+    MPET_REQUIRE(!dist_active(ctx), "multi-GPU GMRES is not built yet (MINRES is; S must be symmetric)");
     KrylovWork* k = get_work(ctx);
     const int64_t n = k->n;
     const int m = ctx->restart;
@@ -461,7 +494,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         initial_residual(ctx, k, st);
         pc_apply_flag(ctx, k->r, k->z, nullptr, st);
         dot_to(ctx, k, k->z, k->z, nullptr, st);
-        k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev);
+        k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev, nullptr);
         LAUNCH_CHECK(ctx);
         double bb = 0;
         CUDA_CHECK(cudaMemcpyAsync(&bb, k->hdev, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -487,7 +520,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
             k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev + 128, -1.0, n, w);
             LAUNCH_CHECK(ctx);
             dot_to(ctx, k, w, w, nullptr, st);
-            k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev + j + 1);
+            k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev + j + 1, nullptr);
             LAUNCH_CHECK(ctx);
             std::vector<double> h1(j + 2), h2(j + 1);
             CUDA_CHECK(cudaMemcpyAsync(h1.data(), k->hdev, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
@@ -547,5 +580,3 @@ void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     else gmres(ctx, b, x, info, st);
 }
 
-void dist_attach(mpet_ctx* ctx, const void*, int, int) { MPET_REQUIRE(false, "multi-GPU attach: not built yet"); }
-void dist_free(mpet_ctx*) {}

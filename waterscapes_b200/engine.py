@@ -157,6 +157,29 @@ class Engine:
     def pc_apply(self, r, z):
         self._ck(self.lib.mpet_pc_apply(self._ctx, _ptr(r), _ptr(z), self._stream()))
 
+    # ------------------------------------------------------------------ multi-GPU
+    def nccl_unique_id(self):
+        buf = (C.c_char * 128)()
+        if self.lib.mpet_nccl_unique_id(C.cast(buf, C.c_void_p)) != 0:
+            raise _lib.MpetLibraryError("ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return bytes(buf.raw)
+
+    def attach_comm(self, uid_bytes, rank, nranks):
+        buf = C.create_string_buffer(uid_bytes, 128)
+        self._ck(self.lib.mpet_attach_comm(self._ctx, C.cast(buf, C.c_void_p), int(rank), int(nranks)))
+
+    def set_halo(self, neighbours, send_lists, recv_lists, owned):
+        n = len(neighbours)
+        ranks = (C.c_int * max(n, 1))(*[int(q) for q in neighbours])
+        soff = np.concatenate([[0], np.cumsum([len(a) for a in send_lists])]).astype(np.int64)
+        roff = np.concatenate([[0], np.cumsum([len(a) for a in recv_lists])]).astype(np.int64)
+        cat = lambda ls: np.concatenate(ls).astype(np.int32) if ls and sum(len(a) for a in ls) else np.zeros(1, np.int32)
+        sd = self._dev(cat(send_lists), torch.int32)
+        rd = self._dev(cat(recv_lists), torch.int32)
+        od = self._dev(np.asarray(owned, dtype=np.uint8), torch.uint8)
+        self._ck(self.lib.mpet_set_halo(self._ctx, n, ranks, (C.c_int64 * (n + 1))(*soff.tolist()), _ptr(sd),
+                                        (C.c_int64 * (n + 1))(*roff.tolist()), _ptr(rd), _ptr(od), self._stream()))
+
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self, reset=False):
         return int(self.lib.mpet_launch_count(self._ctx, int(reset)))

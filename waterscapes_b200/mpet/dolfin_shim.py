@@ -356,6 +356,23 @@ class FunctionSpace:
         self._edges = None
         self._x2 = None
 
+    @classmethod
+    def from_host(cls, mesh, J):
+        """Same layout computed on the host (no engine): edges numbered lexicographically by their
+        sorted vertex pair, exactly what graph.cu builds on the device.  Used by host-only logic/tests."""
+        self = cls.__new__(cls)
+        self.mesh, self.J, self.engine = mesh, J, None
+        c = mesh.cells.astype(np.int64)
+        nv = mesh.num_vertices()
+        pairs = np.concatenate([c[:, [a, b]] for a, b in ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))])
+        keys = np.unique(pairs[:, 0] * nv + pairs[:, 1])
+        self._edges = np.stack([keys // nv, keys % nv], axis=1)
+        self.Nv, self.Ne = nv, keys.shape[0]
+        self.N2 = self.Nv + self.Ne
+        self.N = 3 * self.N2 + J * self.Nv
+        self._x2 = None
+        return self
+
     def dim(self):
         return self.N
 

@@ -31,7 +31,7 @@ def _f(v):
 
 class MPETSolver(object):
 
-    def __init__(self, problem, params=None, device=0):
+    def __init__(self, problem, params=None, device=0, partition=None):
         "Create solver with given MPET problem and parameters."
         self.problem = problem
         self.params = self.default_params()
@@ -44,6 +44,7 @@ class MPETSolver(object):
         if self.params["u_degree"] != 2 or self.params["p_degree"] != 1:
             raise NotImplementedError("the B200 kernels implement the Taylor-Hood pair P2-P1 only")
         self.engine = Engine(device)
+        self.partition = partition          # waterscapes_b200.parallel.Partition (multi-GPU) or None
         self._engine_bc_dofs = None
         self._pc_dirty = True
         self._krylov_cfg = None
@@ -51,6 +52,8 @@ class MPETSolver(object):
         self._facet_ops = {}
         self._lumped = {}
         self.create_variational_forms()
+        if self.partition is not None:
+            self.partition.setup(self.engine, self.VQ, self.problem.mesh)
         self.create_dirichlet_bcs()
 
     # ------------------------------------------------------------------ reference surface
