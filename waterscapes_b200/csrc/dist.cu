@@ -89,12 +89,36 @@ __global__ void k_api_to_internal_idx(const int32_t* __restrict__ in, int64_t n,
     if (i < n) out[i] = (int32_t)api_to_internal(in[i], n2);
 }
 
+__global__ void k_count_holders(const int32_t* __restrict__ idx, int64_t n, double* __restrict__ w) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&w[idx[i]], 1.0);       // integer-valued: order independent
+}
+
+__global__ void k_fill(double* __restrict__ w, int64_t n, double v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) w[i] = v;
+}
+
+__global__ void k_rsqrt(double* __restrict__ w, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) w[i] = 1.0 / sqrt(w[i]);
+}
+
+__global__ void k_scale(const double* __restrict__ w, const double* __restrict__ in, double* __restrict__ out,
+                        int64_t n, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[i] * in[i];
+}
+
 __global__ void k_own_internal(const uint8_t* __restrict__ own_api, int64_t n, int64_t n2, uint8_t* __restrict__ own_int) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) own_int[api_to_internal(i, n2)] = own_api[i];
 }
 
 }  // namespace
+
+void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st);
 
 struct DistState {
     ncclComm_t comm = nullptr;
@@ -106,6 +130,8 @@ struct DistState {
     double* send_buf = nullptr;
     double* recv_buf = nullptr;
     uint8_t* own = nullptr;               // [Nint] 1 on owned dofs (pad lanes 0)
+    double* sqrtw = nullptr;              // [Nint] 1/sqrt(number of ranks holding the dof): partition-of-unity weights
+    double* tmp = nullptr;                // [Nint] weighted residual
 };
 
 void dist_unique_id(void* out128) {
@@ -155,8 +181,26 @@ void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* sen
     CUDA_CHECK(cudaMemsetAsync(d->own, 0, ctx->Nint, st));
     k_own_internal<<<grid_for(ctx->N, 256), 256, 0, st>>>(owned_dev, ctx->N, ctx->N2, d->own);
     LAUNCH_CHECK(ctx);
+    // multiplicity of every dof = 1 + number of neighbours that ghost it; ghosts inherit the owner's value
+    d->sqrtw = dev_alloc<double>(ctx, ctx->Nint);
+    d->tmp = dev_alloc<double>(ctx, ctx->Nint);
+    k_fill<<<grid_for(ctx->Nint, 256), 256, 0, st>>>(d->sqrtw, ctx->Nint, 1.0);
+    LAUNCH_CHECK(ctx);
+    if (ns) { k_count_holders<<<grid_for(ns, 256), 256, 0, st>>>(d->send_idx, ns, d->sqrtw); LAUNCH_CHECK(ctx); }
+    dist_halo(ctx, d->sqrtw, false, nullptr, st);
+    k_rsqrt<<<grid_for(ctx->Nint, 256), 256, 0, st>>>(d->sqrtw, ctx->Nint);
+    LAUNCH_CHECK(ctx);
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
+
+// out = w^(1/2) in   (w = partition-of-unity weights): the symmetric weighting of additive Schwarz
+void dist_weight(mpet_ctx* ctx, const double* in, double* out, const int* done, cudaStream_t st) {
+    DistState* d = ctx->dist;
+    k_scale<<<grid_for(ctx->Nint, 256), 256, 0, st>>>(d->sqrtw, in, out, ctx->Nint, done);
+    LAUNCH_CHECK(ctx);
+}
+
+double* dist_tmp(mpet_ctx* ctx) { return ctx->dist->tmp; }
 
 bool dist_active(mpet_ctx* ctx) { return ctx->dist != nullptr && ctx->dist->nranks > 1; }
 const uint8_t* dist_owned_mask(mpet_ctx* ctx) { return dist_active(ctx) ? ctx->dist->own : nullptr; }

@@ -24,6 +24,8 @@ bool dist_active(mpet_ctx* ctx);
 const uint8_t* dist_owned_mask(mpet_ctx* ctx);
 void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st);
 void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
+void dist_weight(mpet_ctx* ctx, const double* in, double* out, const int* done, cudaStream_t st);
+double* dist_tmp(mpet_ctx* ctx);
 
 
 namespace {
@@ -338,11 +340,17 @@ static void pc_apply_flag(mpet_ctx* ctx, const double* r, double* z, const int* 
 }
 
 static void pc_apply_dist(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
-    pc_apply_flag(ctx, r, z, done, st);
-    if (dist_active(ctx)) {
-        dist_halo(ctx, z, true, done, st);
-        dist_halo(ctx, z, false, done, st);
+    if (!dist_active(ctx)) {
+        pc_apply_flag(ctx, r, z, done, st);
+        return;
     }
+    // z = sum_i R_i^T W_i^(1/2) M_i^-1 W_i^(1/2) R_i r  with W_i the partition-of-unity weights
+    double* t = dist_tmp(ctx);
+    dist_weight(ctx, r, t, done, st);
+    pc_apply_flag(ctx, t, z, done, st);
+    dist_weight(ctx, z, z, done, st);
+    dist_halo(ctx, z, true, done, st);
+    dist_halo(ctx, z, false, done, st);
 }
 
 static void ensure_scratch(mpet_ctx* ctx) {
