@@ -132,18 +132,20 @@ int mpet_pc_apply(mpet_ctx* ctx, const double* r_dev, double* z_dev, void* strea
  * with its OWN cells plus a one-cell ghost layer (no assembly collective is needed), then
  *   mpet_nccl_unique_id : rank 0 creates the 128-byte ncclUniqueId; the host plumbing broadcasts it
  *   mpet_attach_comm    : ncclCommInitRank on this context's device
- *   mpet_set_halo       : neighbour ranks (host, ascending) and, per neighbour q, the LOCAL dof ids
- *                         (numbering of this header) this rank sends to q / receives from q, as two
- *                         concatenated device arrays with host offsets [n_neighbours+1]; both sides list
- *                         a shared dof in the same order.  owned_dev u8[N]: 1 where this rank owns the dof.
- * After that mpet_solve (MINRES) exchanges halos after every SpMV / preconditioner application, counts
- * each dof once in the dot products and all-reduces them; the per-rank V-cycles are combined as an
- * additive Schwarz preconditioner. */
+ *   mpet_set_halo       : neighbour ranks (host, ascending) and, per neighbour q, the LOCAL scalar P2
+ *                         node ids (vertex v -> v, edge e -> Nv + e) whose dofs this rank sends to q /
+ *                         receives from q, as two concatenated device arrays with host offsets
+ *                         [n_neighbours+1]; both sides list a shared node in the same order.
+ *                         owned_nodes_dev u8[N2]: 1 where this rank owns the node (hence all its dofs).
+ * After that mpet_solve (MINRES) refreshes ghost entries after every SpMV, counts each dof once in the
+ * dot products and all-reduces them.  The AMG V-cycles run distributed on the mesh-defined levels (P2, P1:
+ * halo exchange after every smoothing step) and replicated below (restricted residual all-gathered), so the
+ * preconditioner is the same operator for any number of GPUs. */
 int mpet_nccl_unique_id(void* out128_host);
 int mpet_attach_comm(mpet_ctx* ctx, const void* nccl_uid_host, int rank, int nranks);
 int mpet_set_halo(mpet_ctx* ctx, int n_neighbours, const int* ranks_host, const int64_t* send_off_host,
-                  const int32_t* send_dofs_dev, const int64_t* recv_off_host, const int32_t* recv_dofs_dev,
-                  const uint8_t* owned_dev, void* stream);
+                  const int32_t* send_nodes_dev, const int64_t* recv_off_host, const int32_t* recv_nodes_dev,
+                  const uint8_t* owned_nodes_dev, void* stream);
 
 /* ---- instrumentation ---------------------------------------------------------------------------
  * number of kernels this library launched since the last reset (bench.py's "gpu_launches") */

@@ -292,18 +292,18 @@ HostCsr spgemm(const HostCsr& A, const HostCsr& B) {
     return Cm;
 }
 
-// Smoothed-aggregation prolongator for an SPD matrix with possible identity (Dirichlet) rows.
-// Returns P (nrows x naggregates); naggregates == 0 means "cannot coarsen".
-HostCsr sa_prolongator(const HostCsr& A, double theta, int64_t& nagg) {
+// Greedy aggregation (three passes) on the strength graph |a_ij| >= theta sqrt(a_ii a_jj).
+// agg[i] = aggregate of row i or -1 for identity (eliminated Dirichlet) rows.
+void aggregate(const HostCsr& A, double theta, std::vector<int32_t>& agg, int64_t& nagg, std::vector<char>& isolated,
+               std::vector<double>& diag) {
     const int64_t n = A.nrows;
-    std::vector<double> diag(n, 1.0);
+    diag.assign(n, 1.0);
     for (int64_t r = 0; r < n; ++r)
         for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t)
             if (A.ci[t] == r) diag[r] = A.v[t];
-    // strength of connection: |a_ij| >= theta * sqrt(a_ii a_jj)
     std::vector<int32_t> srp(n + 1, 0), sci;
     std::vector<double> sval;
-    std::vector<char> isolated(n, 0);
+    isolated.assign(n, 0);
     for (int64_t r = 0; r < n; ++r) {
         for (int32_t t = A.rp[r]; t < A.rp[r + 1]; ++t) {
             int32_t c = A.ci[t];
@@ -319,10 +319,9 @@ HostCsr sa_prolongator(const HostCsr& A, double theta, int64_t& nagg) {
             if (A.ci[t] != r && A.v[t] != 0.0) { any_off = true; break; }
         isolated[r] = any_off ? 0 : 1;        // identity rows (eliminated Dirichlet dofs) stay out
     }
-    std::vector<int32_t> agg(n, -1);
+    agg.assign(n, -1);
     nagg = 0;
-    // pass 1: seed aggregates from nodes whose whole strong neighbourhood is free
-    for (int64_t r = 0; r < n; ++r) {
+    for (int64_t r = 0; r < n; ++r) {          // pass 1: seeds whose whole strong neighbourhood is free
         if (agg[r] != -1 || isolated[r]) continue;
         bool free_nb = true;
         for (int32_t t = srp[r]; t < srp[r + 1]; ++t)
@@ -332,9 +331,8 @@ HostCsr sa_prolongator(const HostCsr& A, double theta, int64_t& nagg) {
         for (int32_t t = srp[r]; t < srp[r + 1]; ++t) agg[sci[t]] = (int32_t)nagg;
         nagg++;
     }
-    // pass 2: attach leftovers to the most strongly connected neighbouring aggregate
     std::vector<int32_t> agg2(agg);
-    for (int64_t r = 0; r < n; ++r) {
+    for (int64_t r = 0; r < n; ++r) {          // pass 2: attach leftovers to the strongest neighbouring aggregate
         if (agg[r] != -1 || isolated[r]) continue;
         double best = -1; int32_t who = -1;
         for (int32_t t = srp[r]; t < srp[r + 1]; ++t)
@@ -342,14 +340,23 @@ HostCsr sa_prolongator(const HostCsr& A, double theta, int64_t& nagg) {
         if (who >= 0) agg2[r] = who;
     }
     agg.swap(agg2);
-    // pass 3: what is still free forms new aggregates with its free strong neighbours
-    for (int64_t r = 0; r < n; ++r) {
+    for (int64_t r = 0; r < n; ++r) {          // pass 3: the rest forms new aggregates
         if (agg[r] != -1 || isolated[r]) continue;
         agg[r] = (int32_t)nagg;
         for (int32_t t = srp[r]; t < srp[r + 1]; ++t)
             if (agg[sci[t]] == -1 && !isolated[sci[t]]) agg[sci[t]] = (int32_t)nagg;
         nagg++;
     }
+}
+
+// Smoothed-aggregation prolongator for an SPD matrix with possible identity (Dirichlet) rows.
+// Returns P (nrows x naggregates); naggregates == 0 means "cannot coarsen".
+HostCsr sa_prolongator(const HostCsr& A, double theta, int64_t& nagg) {
+    const int64_t n = A.nrows;
+    std::vector<int32_t> agg;
+    std::vector<char> isolated;
+    std::vector<double> diag;
+    aggregate(A, theta, agg, nagg, isolated, diag);
     HostCsr P;
     if (nagg == 0) return P;
     // tentative prolongator (piecewise constant), then one damped-Jacobi smoothing step
@@ -514,6 +521,8 @@ void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, 
         }
         if (bounce)
             CUDA_CHECK(cudaMemcpyAsync(x_out, dst, sizeof(double) * n * W, cudaMemcpyDeviceToDevice, st));
+        // distributed level: owned rows are right, ghost rows are refreshed from their owners
+        if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, bounce ? x_out : dst, false, done, st);
         cur = dst;
     }
 }
@@ -534,11 +543,20 @@ void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x,
     AmgLevel& C = H.levels[lev + 1];
     const int64_t nc = C.A.nrows;
     chebyshev<W>(ctx, L, b, nullptr, x, done, st);                                            // pre-smooth
-    launch_epi<W, EPI_RESID>(ctx, L.A, L.planA, x, b, L.t, nullptr, nullptr, 0, 0, done, st);           // residual
-    launch_plain<W>(ctx, C.R, C.planR, L.t, C.b, 0.0, done, st);                                        // restrict
+    launch_epi<W, EPI_RESID>(ctx, L.A, L.planA, x, b, L.t, nullptr, nullptr, 0, 0, done, st);  // residual
+    if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, L.t, false, done, st);
+    if (lev == H.transition) {
+        // restrict onto this rank's aggregates, all-gather the padded slots: coarser levels are replicated
+        launch_plain<W>(ctx, C.R, C.planR, L.t, H.gather_send, 0.0, done, st);
+        dist_allgather(ctx, H.gather_send, C.b, H.gather_count * W, st);
+    } else {
+        launch_plain<W>(ctx, C.R, C.planR, L.t, C.b, 0.0, done, st);                           // restrict
+        if (C.halo_plan >= 0) dist_halo(ctx, C.halo_plan, C.b, false, done, st);
+    }
     double* xc = C.x + (int64_t)W * nc;   // second half of the coarse x buffer holds the coarse solution
     vcycle<W>(ctx, H, lev + 1, C.b, xc, done, st);
-    launch_plain<W>(ctx, C.P, C.planP, xc, x, 1.0, done, st);                                           // prolong + correct
+    launch_plain<W>(ctx, C.P, C.planP, xc, x, 1.0, done, st);                                  // prolong + correct
+    if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, x, false, done, st);
     chebyshev<W>(ctx, L, b, x, x, done, st);                                                   // post-smooth
 }
 
@@ -587,6 +605,15 @@ double estimate_lambda_max(mpet_ctx* ctx, AmgLevel& L, cudaStream_t st) {
     cudaFree(tmp); cudaFree(x); cudaFree(y);
     double est = 1.1 * lam;
     if (est <= 0 || est > gersh) est = gersh;
+    if (L.halo_plan >= 0 && dist_active(ctx)) {     // every rank must run the same smoother
+        double* dv = nullptr;
+        CUDA_CHECK(cudaMalloc(&dv, sizeof(double)));
+        CUDA_CHECK(cudaMemcpy(dv, &est, sizeof(double), cudaMemcpyHostToDevice));
+        dist_allreduce_max(ctx, dv, 1, st);
+        CUDA_CHECK(cudaMemcpyAsync(&est, dv, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(dv);
+    }
     return est;
 }
 
@@ -600,9 +627,159 @@ void compute_dinv_host(mpet_ctx* ctx, AmgLevel& L, const HostCsr& H) {
 }
 
 // extend H below its current last level (whose A is on device) by smoothed aggregation
+void compute_dinv_host(mpet_ctx* ctx, AmgLevel& L, const HostCsr& H);
+
+template <typename T>
+void bcast_vector(mpet_ctx* ctx, std::vector<T>& v, int64_t count, int root, cudaStream_t st) {
+    v.resize(count);
+    if (count == 0) return;
+    T* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, sizeof(T) * count));
+    if (dist_rank(ctx) == root) CUDA_CHECK(cudaMemcpy(d, v.data(), sizeof(T) * count, cudaMemcpyHostToDevice));
+    dist_bcast_bytes(ctx, d, (int64_t)sizeof(T) * count, root, st);
+    CUDA_CHECK(cudaMemcpyAsync(v.data(), d, sizeof(T) * count, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d);
+}
+
+// Multi-GPU: from the last mesh-defined (distributed) level to the first replicated one.  Every rank
+// aggregates its OWNED vertices (plain aggregation, so the prolongator needs no neighbour data), learns
+// the global aggregate id of its ghost vertices through one halo exchange, forms its rows of the
+// Galerkin matrix from its complete owned rows, and the row blocks are broadcast to everybody.  The
+// replicated numbering is padded: rank r's aggregates are r*maxcount .. r*maxcount+nagg_r-1, padding
+// rows are identity rows.
+HostCsr distributed_transition(mpet_ctx* ctx, AmgHierarchy& H, int W, cudaStream_t st) {
+    AmgLevel& F = H.levels.back();
+    HostCsr A = download(F.A);
+    const int64_t n = A.nrows;
+    const std::vector<uint8_t>& ownn = dist_own_nodes(ctx);     // vertices are the first n nodes
+    const int rank = dist_rank(ctx), nr = dist_nranks(ctx);
+    std::vector<int32_t> l2o(n, -1), o2l;
+    for (int64_t i = 0; i < n; ++i)
+        if (ownn[i]) { l2o[i] = (int32_t)o2l.size(); o2l.push_back((int32_t)i); }
+    HostCsr Aoo;
+    Aoo.nrows = Aoo.ncols = (int64_t)o2l.size();
+    Aoo.rp.assign(Aoo.nrows + 1, 0);
+    for (int64_t o = 0; o < Aoo.nrows; ++o) {
+        const int32_t i = o2l[o];
+        for (int32_t t = A.rp[i]; t < A.rp[i + 1]; ++t)
+            if (l2o[A.ci[t]] >= 0) { Aoo.ci.push_back(l2o[A.ci[t]]); Aoo.v.push_back(A.v[t]); }
+        Aoo.rp[o + 1] = (int32_t)Aoo.ci.size();
+    }
+    std::vector<int32_t> agg;
+    std::vector<char> isolated;
+    std::vector<double> diag;
+    int64_t nagg = 0;
+    aggregate(Aoo, 0.08, agg, nagg, isolated, diag);
+    // padded slot size = max aggregate count over ranks
+    double* dcnt = nullptr;
+    CUDA_CHECK(cudaMalloc(&dcnt, sizeof(double)));
+    double cnt = (double)nagg;
+    CUDA_CHECK(cudaMemcpy(dcnt, &cnt, sizeof(double), cudaMemcpyHostToDevice));
+    dist_allreduce_max(ctx, dcnt, 1, st);
+    CUDA_CHECK(cudaMemcpyAsync(&cnt, dcnt, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(dcnt);
+    const int64_t maxcount = (int64_t)cnt;
+    MPET_REQUIRE(maxcount > 0 && maxcount * nr < 2147483647LL, "bad aggregate counts");
+    H.gather_count = maxcount;
+    // global (padded) aggregate id of every local vertex: owned from the aggregation, ghosts via halo
+    std::vector<double> g(n, -1.0);
+    for (int64_t o = 0; o < Aoo.nrows; ++o)
+        if (agg[o] >= 0) g[o2l[o]] = (double)(rank * maxcount + agg[o]);
+    double* dg = nullptr;
+    CUDA_CHECK(cudaMalloc(&dg, sizeof(double) * n));
+    CUDA_CHECK(cudaMemcpy(dg, g.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    dist_halo(ctx, DIST_PLAN_P1W1, dg, false, nullptr, st);
+    CUDA_CHECK(cudaMemcpyAsync(g.data(), dg, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(dg);
+    // my rows of the Galerkin matrix (unit prolongator weights)
+    struct Trip { int32_t r, c; double v; };
+    std::vector<Trip> trips;
+    for (int64_t o = 0; o < Aoo.nrows; ++o) {
+        if (agg[o] < 0) continue;
+        const int32_t i = o2l[o];
+        for (int32_t t = A.rp[i]; t < A.rp[i + 1]; ++t) {
+            const double gj = g[A.ci[t]];
+            if (gj < 0 || A.v[t] == 0.0) continue;
+            trips.push_back({agg[o], (int32_t)gj, A.v[t]});
+        }
+    }
+    std::sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+    std::vector<int32_t> my_rp(nagg + 1, 0), my_ci;
+    std::vector<double> my_v;
+    for (size_t t = 0; t < trips.size();) {
+        size_t u = t;
+        double sum = 0;
+        while (u < trips.size() && trips[u].r == trips[t].r && trips[u].c == trips[t].c) sum += trips[u++].v;
+        my_ci.push_back(trips[t].c);
+        my_v.push_back(sum);
+        my_rp[trips[t].r + 1] = (int32_t)my_ci.size();
+        t = u;
+    }
+    for (int64_t r = 0; r < nagg; ++r) my_rp[r + 1] = std::max(my_rp[r + 1], my_rp[r]);
+    // replicate: every rank broadcasts its row block
+    HostCsr Ac;
+    Ac.nrows = Ac.ncols = maxcount * nr;
+    Ac.rp.assign(Ac.nrows + 1, 0);
+    for (int root = 0; root < nr; ++root) {
+        std::vector<int64_t> hdr(2);
+        if (root == rank) { hdr[0] = nagg; hdr[1] = (int64_t)my_ci.size(); }
+        bcast_vector(ctx, hdr, 2, root, st);
+        std::vector<int32_t> rp, ci;
+        std::vector<double> vv;
+        if (root == rank) { rp = my_rp; ci = my_ci; vv = my_v; }
+        bcast_vector(ctx, rp, hdr[0] + 1, root, st);
+        bcast_vector(ctx, ci, hdr[1], root, st);
+        bcast_vector(ctx, vv, hdr[1], root, st);
+        for (int64_t r = 0; r < maxcount; ++r) {
+            const int64_t grow = root * maxcount + r;
+            if (r < hdr[0]) {
+                for (int32_t t = rp[r]; t < rp[r + 1]; ++t) { Ac.ci.push_back(ci[t]); Ac.v.push_back(vv[t]); }
+            } else {
+                Ac.ci.push_back((int32_t)grow);      // padding: identity row
+                Ac.v.push_back(1.0);
+            }
+            Ac.rp[grow + 1] = (int32_t)Ac.ci.size();
+        }
+    }
+    // transfer operators of this rank: P (local vertices x replicated rows), R (my padded slot x local vertices)
+    HostCsr P, R;
+    P.nrows = n; P.ncols = Ac.nrows;
+    P.rp.assign(n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (ownn[i] && g[i] >= 0) { P.ci.push_back((int32_t)g[i]); P.v.push_back(1.0); }
+        P.rp[i + 1] = (int32_t)P.ci.size();
+    }
+    R.nrows = maxcount; R.ncols = n;
+    std::vector<std::vector<int32_t>> members(maxcount);
+    for (int64_t o = 0; o < Aoo.nrows; ++o)
+        if (agg[o] >= 0) members[agg[o]].push_back(o2l[o]);
+    R.rp.assign(maxcount + 1, 0);
+    for (int64_t r = 0; r < maxcount; ++r) {
+        for (int32_t m : members[r]) { R.ci.push_back(m); R.v.push_back(1.0); }
+        R.rp[r + 1] = (int32_t)R.ci.size();
+    }
+    AmgLevel L;
+    L.A = upload(ctx, Ac);
+    L.P = upload(ctx, P);
+    L.R = upload(ctx, R);
+    compute_dinv_host(ctx, L, Ac);
+    H.levels.push_back(L);
+    H.gather_send = dev_alloc<double>(ctx, maxcount * W);
+    return Ac;
+}
+
 void extend_by_aggregation(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
     CUDA_CHECK(cudaStreamSynchronize(st));
-    HostCsr A = download(H.levels.back().A);
+    HostCsr A;
+    if (dist_active(ctx)) {
+        H.transition = (int)H.levels.size() - 1;
+        A = distributed_transition(ctx, H, H.nrhs, st);
+    } else {
+        A = download(H.levels.back().A);
+    }
     double theta = 0.08;
     while (A.nrows > kCoarseMax && (int)H.levels.size() < kMaxLevels) {
         int64_t nagg = 0;
@@ -716,10 +893,12 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         H->nrhs = 4;   // W = 4: three components + pad
         AmgLevel L0;
         L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->mu, ctx->bc_mask, &L0.dinv, st);
+        if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P2W4;
         H->levels.push_back(L0);
         AmgLevel L1;
         L1.A = masked_block(ctx, ctx->g11, ctx->l11, ctx->mu, ctx->bc_mask /* vertices are the first Nv nodes */,
                             &L1.dinv, st);
+        if (dist_active(ctx)) L1.halo_plan = DIST_PLAN_P1W4;
         HostCsr P = p2_to_p1(nv, ctx->Ne, edge_v, mask2);
         L1.P = upload(ctx, P);
         L1.R = upload(ctx, transpose(P));
@@ -735,6 +914,7 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         AmgLevel L0;
         L0.A = masked_block(ctx, ctx->g11, ctx->pp11 + (int64_t)i * ctx->g11.nnz, 1.0,
                             ctx->bc_mask + 3 * n2 + (int64_t)i * nv, &L0.dinv, st);
+        if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P1W1;
         H->levels.push_back(L0);
         extend_by_aggregation(ctx, *H, st);
         finish_hierarchy(ctx, *H, st);

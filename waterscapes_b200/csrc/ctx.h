@@ -65,6 +65,7 @@ struct AmgLevel {
     double* r = nullptr;
     double* t = nullptr;
     double lambda_max = 0.0;  // estimate of rho(D^-1 A)
+    int halo_plan = -1;       // >= 0: level vectors are distributed (owned + ghost rows), refreshed with this plan
     SpmmPlan planA, planP, planR;   // staged-kernel chunk tables (nchunks == 0: not staged)
 };
 
@@ -73,6 +74,9 @@ struct AmgHierarchy {
     int nrhs = 1;
     double* coarse_inv = nullptr;  // dense inverse on the coarsest level
     int64_t coarse_n = 0;
+    int transition = -1;           // multi-GPU: index of the last distributed level (coarser ones are replicated)
+    int64_t gather_count = 0;      // rows per rank in the padded replicated numbering
+    double* gather_send = nullptr; // [gather_count * W] local slot of the all-gathered coarse right-hand side
 };
 
 // CUDA-event profiler: per-category device time of the launches made inside the library
@@ -206,6 +210,18 @@ bool staged_block_spmv(mpet_ctx* ctx, const double* x, double* y, const uint8_t*
 bool staged_build_spmm_plan(mpet_ctx* ctx, const std::vector<int32_t>& rp, SpmmPlan& plan);
 void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
                  double* out, double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st);
+// dist.cu (multi-GPU)
+enum { DIST_PLAN_KRYLOV = 0, DIST_PLAN_P2W4 = 1, DIST_PLAN_P1W4 = 2, DIST_PLAN_P1W1 = 3, DIST_NPLANS = 4 };
+bool dist_active(mpet_ctx* ctx);
+int dist_rank(mpet_ctx* ctx);
+int dist_nranks(mpet_ctx* ctx);
+const uint8_t* dist_owned_mask(mpet_ctx* ctx);
+const std::vector<uint8_t>& dist_own_nodes(mpet_ctx* ctx);
+void dist_halo(mpet_ctx* ctx, int plan, double* v, bool reverse, const int* done, cudaStream_t st);
+void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
+void dist_allreduce_max(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
+void dist_allgather(mpet_ctx* ctx, const double* send, double* recv, int64_t count, cudaStream_t st);
+void dist_bcast_bytes(mpet_ctx* ctx, void* buf, int64_t nbytes, int root, cudaStream_t st);
 // spmv.cu
 void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,
               const double* vals, const double* x, double* y, double beta, const uint8_t* rowmask,

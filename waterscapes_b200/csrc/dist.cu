@@ -20,7 +20,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
 struct NcclApi {
     void* handle = nullptr;
@@ -32,6 +32,8 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
 
@@ -54,6 +56,8 @@ void load_nccl() {
     RESOLVE(Send, "ncclSend")
     RESOLVE(Recv, "ncclRecv")
     RESOLVE(AllReduce, "ncclAllReduce")
+    RESOLVE(AllGather, "ncclAllGather")
+    RESOLVE(Broadcast, "ncclBroadcast")
     RESOLVE(GetErrorString, "ncclGetErrorString")
 #undef RESOLVE
 }
@@ -118,20 +122,21 @@ __global__ void k_own_internal(const uint8_t* __restrict__ own_api, int64_t n, i
 
 }  // namespace
 
-void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st);
+struct HaloPlan {
+    std::vector<int64_t> send_off, recv_off;   // [nnbr+1]
+    int32_t* send_idx = nullptr;               // entries of owned dofs a neighbour ghosts
+    int32_t* recv_idx = nullptr;               // entries of my ghost dofs
+};
 
 struct DistState {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     std::vector<int> nbr;                 // neighbour ranks (ascending)
-    std::vector<int64_t> send_off, recv_off;   // [nnbr+1]
-    int32_t* send_idx = nullptr;          // internal-layout indices of owned dofs a neighbour needs
-    int32_t* recv_idx = nullptr;          // internal-layout indices of my ghost dofs
+    HaloPlan plan[DIST_NPLANS];           // Krylov vectors, P2 x W4, P1 x W4, P1 x W1 level vectors
     double* send_buf = nullptr;
     double* recv_buf = nullptr;
     uint8_t* own = nullptr;               // [Nint] 1 on owned dofs (pad lanes 0)
-    double* sqrtw = nullptr;              // [Nint] 1/sqrt(number of ranks holding the dof): partition-of-unity weights
-    double* tmp = nullptr;                // [Nint] weighted residual
+    std::vector<uint8_t> own_nodes;       // host copy: ownership of the scalar P2 nodes (vertices first)
 };
 
 void dist_unique_id(void* out128) {
@@ -161,59 +166,81 @@ void dist_free(mpet_ctx* ctx) {
     ctx->dist = nullptr;
 }
 
-// dof indices arrive in the API (UFC) numbering of the LOCAL mesh
-void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* send_off, const int32_t* send_idx_dev,
-                   const int64_t* recv_off, const int32_t* recv_idx_dev, const uint8_t* owned_dev, cudaStream_t st) {
+// Node lists arrive per neighbour (scalar P2 node ids of the LOCAL mesh, vertices are ids < Nv), both
+// sides listing a shared node in the same order.  Four index plans are derived from them.
+void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* send_off, const int32_t* send_nodes_dev,
+                   const int64_t* recv_off, const int32_t* recv_nodes_dev, const uint8_t* owned_nodes_dev,
+                   cudaStream_t st) {
     MPET_REQUIRE(ctx->dist != nullptr, "mpet_attach_comm must be called first");
     MPET_REQUIRE(ctx->N > 0, "mpet_set_mesh must be called first");
     DistState* d = ctx->dist;
-    d->nbr.assign(ranks, ranks + nnbr);
-    d->send_off.assign(send_off, send_off + nnbr + 1);
-    d->recv_off.assign(recv_off, recv_off + nnbr + 1);
-    const int64_t ns = d->send_off[nnbr], nr = d->recv_off[nnbr];
-    d->send_idx = dev_alloc<int32_t>(ctx, ns);
-    d->recv_idx = dev_alloc<int32_t>(ctx, nr);
-    d->send_buf = dev_alloc<double>(ctx, std::max<int64_t>(ns, nr));
-    d->recv_buf = dev_alloc<double>(ctx, std::max<int64_t>(ns, nr));
-    d->own = dev_alloc<uint8_t>(ctx, ctx->Nint);
-    if (ns) { k_api_to_internal_idx<<<grid_for(ns, 256), 256, 0, st>>>(send_idx_dev, ns, ctx->N2, d->send_idx); LAUNCH_CHECK(ctx); }
-    if (nr) { k_api_to_internal_idx<<<grid_for(nr, 256), 256, 0, st>>>(recv_idx_dev, nr, ctx->N2, d->recv_idx); LAUNCH_CHECK(ctx); }
-    CUDA_CHECK(cudaMemsetAsync(d->own, 0, ctx->Nint, st));
-    k_own_internal<<<grid_for(ctx->N, 256), 256, 0, st>>>(owned_dev, ctx->N, ctx->N2, d->own);
-    LAUNCH_CHECK(ctx);
-    // multiplicity of every dof = 1 + number of neighbours that ghost it; ghosts inherit the owner's value
-    d->sqrtw = dev_alloc<double>(ctx, ctx->Nint);
-    d->tmp = dev_alloc<double>(ctx, ctx->Nint);
-    k_fill<<<grid_for(ctx->Nint, 256), 256, 0, st>>>(d->sqrtw, ctx->Nint, 1.0);
-    LAUNCH_CHECK(ctx);
-    if (ns) { k_count_holders<<<grid_for(ns, 256), 256, 0, st>>>(d->send_idx, ns, d->sqrtw); LAUNCH_CHECK(ctx); }
-    dist_halo(ctx, d->sqrtw, false, nullptr, st);
-    k_rsqrt<<<grid_for(ctx->Nint, 256), 256, 0, st>>>(d->sqrtw, ctx->Nint);
-    LAUNCH_CHECK(ctx);
     CUDA_CHECK(cudaStreamSynchronize(st));
+    d->nbr.assign(ranks, ranks + nnbr);
+    const int64_t n2 = ctx->N2, nv = ctx->Nv;
+    const int A = ctx->A;
+    std::vector<int32_t> sn(send_off[nnbr]), rn(recv_off[nnbr]);
+    if (!sn.empty()) CUDA_CHECK(cudaMemcpy(sn.data(), send_nodes_dev, sizeof(int32_t) * sn.size(), cudaMemcpyDeviceToHost));
+    if (!rn.empty()) CUDA_CHECK(cudaMemcpy(rn.data(), recv_nodes_dev, sizeof(int32_t) * rn.size(), cudaMemcpyDeviceToHost));
+    d->own_nodes.resize(n2);
+    CUDA_CHECK(cudaMemcpy(d->own_nodes.data(), owned_nodes_dev, n2, cudaMemcpyDeviceToHost));
+    int64_t maxlen = 1;
+    for (int pl = 0; pl < DIST_NPLANS; ++pl) {
+        HaloPlan& P = d->plan[pl];
+        auto build = [&](const std::vector<int32_t>& nodes, const int64_t* off, std::vector<int64_t>& poff,
+                         int32_t** dev) {
+            std::vector<int32_t> idx;
+            poff.assign(nnbr + 1, 0);
+            for (int q = 0; q < nnbr; ++q) {
+                for (int64_t t = off[q]; t < off[q + 1]; ++t) {
+                    const int32_t a = nodes[t];
+                    const bool vertex = a < nv;
+                    switch (pl) {
+                        case DIST_PLAN_KRYLOV:
+                        case DIST_PLAN_P2W4: for (int k = 0; k < 3; ++k) idx.push_back(4 * a + k); break;
+                        case DIST_PLAN_P1W4: if (vertex) for (int k = 0; k < 3; ++k) idx.push_back(4 * a + k); break;
+                        case DIST_PLAN_P1W1: if (vertex) idx.push_back(a); break;
+                    }
+                }
+                if (pl == DIST_PLAN_KRYLOV)
+                    for (int i = 0; i < A; ++i)
+                        for (int64_t t = off[q]; t < off[q + 1]; ++t)
+                            if (nodes[t] < nv) idx.push_back((int32_t)(4 * n2 + (int64_t)i * nv + nodes[t]));
+                poff[q + 1] = (int64_t)idx.size();
+            }
+            *dev = dev_alloc<int32_t>(ctx, (int64_t)idx.size());
+            if (!idx.empty()) CUDA_CHECK(cudaMemcpy(*dev, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice));
+            maxlen = std::max<int64_t>(maxlen, (int64_t)idx.size());
+        };
+        build(sn, send_off, P.send_off, &P.send_idx);
+        build(rn, recv_off, P.recv_off, &P.recv_idx);
+    }
+    d->send_buf = dev_alloc<double>(ctx, maxlen);
+    d->recv_buf = dev_alloc<double>(ctx, maxlen);
+    // ownership mask of the Krylov vectors (solver-internal layout; pad lanes stay 0)
+    std::vector<uint8_t> own(ctx->Nint, 0);
+    for (int64_t a = 0; a < n2; ++a)
+        if (d->own_nodes[a]) {
+            own[4 * a] = own[4 * a + 1] = own[4 * a + 2] = 1;
+            if (a < nv)
+                for (int i = 0; i < A; ++i) own[4 * n2 + (int64_t)i * nv + a] = 1;
+        }
+    d->own = dev_alloc<uint8_t>(ctx, ctx->Nint);
+    CUDA_CHECK(cudaMemcpy(d->own, own.data(), ctx->Nint, cudaMemcpyHostToDevice));
 }
-
-// out = w^(1/2) in   (w = partition-of-unity weights): the symmetric weighting of additive Schwarz
-void dist_weight(mpet_ctx* ctx, const double* in, double* out, const int* done, cudaStream_t st) {
-    DistState* d = ctx->dist;
-    k_scale<<<grid_for(ctx->Nint, 256), 256, 0, st>>>(d->sqrtw, in, out, ctx->Nint, done);
-    LAUNCH_CHECK(ctx);
-}
-
-double* dist_tmp(mpet_ctx* ctx) { return ctx->dist->tmp; }
 
 bool dist_active(mpet_ctx* ctx) { return ctx->dist != nullptr && ctx->dist->nranks > 1; }
 const uint8_t* dist_owned_mask(mpet_ctx* ctx) { return dist_active(ctx) ? ctx->dist->own : nullptr; }
 
 // forward: owners -> ghosts (copy).  reverse: ghosts -> owners (add).
-void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st) {
+void dist_halo(mpet_ctx* ctx, int plan, double* v, bool reverse, const int* done, cudaStream_t st) {
     if (!dist_active(ctx)) return;
     DistState* d = ctx->dist;
+    const HaloPlan& P = d->plan[plan];
     const int nn = (int)d->nbr.size();
-    const int32_t* pack_idx = reverse ? d->recv_idx : d->send_idx;
-    const int32_t* unpack_idx = reverse ? d->send_idx : d->recv_idx;
-    const std::vector<int64_t>& poff = reverse ? d->recv_off : d->send_off;
-    const std::vector<int64_t>& uoff = reverse ? d->send_off : d->recv_off;
+    const int32_t* pack_idx = reverse ? P.recv_idx : P.send_idx;
+    const int32_t* unpack_idx = reverse ? P.send_idx : P.recv_idx;
+    const std::vector<int64_t>& poff = reverse ? P.recv_off : P.send_off;
+    const std::vector<int64_t>& uoff = reverse ? P.send_off : P.recv_off;
     const int64_t np = poff[nn], nu = uoff[nn];
     if (np) { k_pack<<<grid_for(np, 256), 256, 0, st>>>(pack_idx, np, v, d->send_buf, done); LAUNCH_CHECK(ctx); }
     NCCL_CHECK(g_nccl.GroupStart());
@@ -224,8 +251,7 @@ void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStre
     }
     NCCL_CHECK(g_nccl.GroupEnd());
     if (reverse) {
-        // one kernel per neighbour, in rank order: a dof ghosted by two neighbours is summed deterministically
-        for (int q = 0; q < nn; ++q) {
+        for (int q = 0; q < nn; ++q) {      // rank order: deterministic sums
             const int64_t cr = uoff[q + 1] - uoff[q];
             if (cr) { k_unpack<<<grid_for(cr, 256), 256, 0, st>>>(unpack_idx + uoff[q], cr, d->recv_buf + uoff[q], v, 1, done); LAUNCH_CHECK(ctx); }
         }
@@ -233,6 +259,23 @@ void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStre
         k_unpack<<<grid_for(nu, 256), 256, 0, st>>>(unpack_idx, nu, d->recv_buf, v, 0, done);
         LAUNCH_CHECK(ctx);
     }
+}
+
+int dist_rank(mpet_ctx* ctx) { return ctx->dist ? ctx->dist->rank : 0; }
+int dist_nranks(mpet_ctx* ctx) { return ctx->dist ? ctx->dist->nranks : 1; }
+const std::vector<uint8_t>& dist_own_nodes(mpet_ctx* ctx) { return ctx->dist->own_nodes; }
+
+// equal-count all-gather of doubles (device buffers)
+void dist_allgather(mpet_ctx* ctx, const double* send, double* recv, int64_t count, cudaStream_t st) {
+    NCCL_CHECK(g_nccl.AllGather(send, recv, (size_t)count, NCCL_FLOAT64, ctx->dist->comm, st));
+}
+// broadcast of raw bytes (device buffer) from `root`
+void dist_bcast_bytes(mpet_ctx* ctx, void* buf, int64_t nbytes, int root, cudaStream_t st) {
+    NCCL_CHECK(g_nccl.Broadcast(buf, buf, (size_t)nbytes, NCCL_INT8, root, ctx->dist->comm, st));
+}
+void dist_allreduce_max(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st) {
+    if (!dist_active(ctx)) return;
+    NCCL_CHECK(g_nccl.AllReduce(dev_scalars, dev_scalars, (size_t)count, NCCL_FLOAT64, NCCL_MAX, ctx->dist->comm, st));
 }
 
 void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st) {

@@ -19,13 +19,7 @@
 #include <vector>
 
 void scatter_bc_values_int(mpet_ctx* ctx, double* out_int, cudaStream_t st);   // rhs.cu
-// multi-GPU hooks (dist.cu)
-bool dist_active(mpet_ctx* ctx);
-const uint8_t* dist_owned_mask(mpet_ctx* ctx);
-void dist_halo(mpet_ctx* ctx, double* v, bool reverse, const int* done, cudaStream_t st);
-void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
-void dist_weight(mpet_ctx* ctx, const double* in, double* out, const int* done, cudaStream_t st);
-double* dist_tmp(mpet_ctx* ctx);
+// multi-GPU hooks: see ctx.h (dist.cu)
 
 
 namespace {
@@ -340,17 +334,9 @@ static void pc_apply_flag(mpet_ctx* ctx, const double* r, double* z, const int* 
 }
 
 static void pc_apply_dist(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
-    if (!dist_active(ctx)) {
-        pc_apply_flag(ctx, r, z, done, st);
-        return;
-    }
-    // z = sum_i R_i^T W_i^(1/2) M_i^-1 W_i^(1/2) R_i r  with W_i the partition-of-unity weights
-    double* t = dist_tmp(ctx);
-    dist_weight(ctx, r, t, done, st);
-    pc_apply_flag(ctx, t, z, done, st);
-    dist_weight(ctx, z, z, done, st);
-    dist_halo(ctx, z, true, done, st);
-    dist_halo(ctx, z, false, done, st);
+    // the V-cycles exchange their own halos level by level (amg.cu); one more refresh covers Jacobi / none
+    pc_apply_flag(ctx, r, z, done, st);
+    if (dist_active(ctx) && ctx->pc != 2) dist_halo(ctx, DIST_PLAN_KRYLOV, z, false, done, st);
 }
 
 static void ensure_scratch(mpet_ctx* ctx) {
@@ -387,21 +373,18 @@ static void dot_to(mpet_ctx* ctx, KrylovWork* k, const double* a, const double* 
     finish_reduction(ctx, k, done, st);
 }
 
-// z = M^-1 r.  Multi-GPU: additive Schwarz over the overlapping per-rank blocks -- every rank applies its
-// local V-cycles, ghost contributions are ADDED into the owners (reverse halo), owners are copied back
-// to the ghosts (forward halo).  Symmetric and positive definite, as MINRES needs.
 static void pc_apply_dist(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st);
 
 
 // xi (internal layout) carries the Dirichlet values; r = b - A x on free rows, 0 on Dirichlet rows
 static void initial_residual(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
     if (ctx->n_bc > 0) scatter_bc_values_int(ctx, k->xi, st);
-    dist_halo(ctx, k->xi, false, nullptr, st);      // ghosts of x and b come from their owners
-    dist_halo(ctx, k->bi, false, nullptr, st);
+    dist_halo(ctx, DIST_PLAN_KRYLOV, k->xi, false, nullptr, st);      // ghosts of x and b come from their owners
+    dist_halo(ctx, DIST_PLAN_KRYLOV, k->bi, false, nullptr, st);
     block_spmv(ctx, k->xi, k->v, nullptr, nullptr, st);
     k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr, k->n, k->r);
     LAUNCH_CHECK(ctx);
-    dist_halo(ctx, k->r, false, nullptr, st);       // ghost rows of the local matrix are incomplete
+    dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);       // ghost rows of the local matrix are incomplete
 }
 
 static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
@@ -426,7 +409,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
             cudaEvent_t pe = prof_begin(ctx, st);
             block_spmv(ctx, k->u, k->r, mask, done, st);
             prof_end(ctx, PROF_SPMV, pe, st);
-            dist_halo(ctx, k->r, false, done, st);
+            dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, done, st);
             dot_to(ctx, k, k->r, k->u, done, st);
             k_minres_alpha<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
             LAUNCH_CHECK(ctx);

@@ -168,6 +168,10 @@ class Partition:
             parts = [k * N2 + nodes for k in range(3)] + [3 * N2 + i * Nv + verts for i in range(J)]
             return np.concatenate(parts).astype(np.int32)
 
+        empty = np.zeros(0, dtype=np.int64)
+        self.send_nodes = {q: send_nodes.get(q, empty).astype(np.int32) for q in self.neighbours}
+        self.recv_nodes = {q: (need[q][0] if q in need else empty).astype(np.int32) for q in self.neighbours}
+        # dof-level lists in the UFC numbering (host-side checks; the library derives its own from the nodes)
         self.send = {q: dofs_of(send_nodes.get(q, np.zeros(0, dtype=np.int64))) for q in self.neighbours}
         self.recv = {q: dofs_of(need[q][0] if q in need else np.zeros(0, dtype=np.int64)) for q in self.neighbours}
         owned = np.zeros(space.N, dtype=np.uint8)
@@ -187,8 +191,8 @@ class Partition:
             uid[0] = engine.nccl_unique_id()
         dist.broadcast_object_list(uid, src=0, group=self.group)
         engine.attach_comm(uid[0], self.rank, self.nranks)
-        engine.set_halo(self.neighbours, [self.send[q] for q in self.neighbours],
-                        [self.recv[q] for q in self.neighbours], self.owned_dofs)
+        engine.set_halo(self.neighbours, [self.send_nodes[q] for q in self.neighbours],
+                        [self.recv_nodes[q] for q in self.neighbours], self.owned_nodes.astype(np.uint8))
         return self
 
     def n_owned_dofs(self):
