@@ -1,23 +1,31 @@
 // Shared-memory-staged sparse kernels: the matrix stream is moved by the bulk-async copy engine
 // (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), warps only gather and reduce.
 //
-// Why (profiles/r01_*): the warp-per-row kernels are latency-bound.  Each warp walks a chain of
-// dependent DRAM round trips (row pointers -> values/indices -> gather -> epilogue operands) and
-// register pressure caps occupancy, so only ~1/3 of HBM bandwidth is reached.  Here a persistent CTA
-// owns a double-buffered ring of stages; one elected thread asks the copy engine for the next chunk
-// (a run of consecutive rows whose values, column indices and row pointers are CONTIGUOUS in memory),
-// while the eight warps consume the previous chunk out of shared memory.  The only long-latency
-// operation left in a warp is the 256-bit gather of the neighbour's vector entries.
+// Why (profiles/r01_*): warp-per-row kernels are latency-bound.  Each warp walks a chain of dependent
+// DRAM round trips (row pointers -> values/indices -> gather -> epilogue operands), so only ~1/3 of HBM
+// bandwidth is reached.  Here a persistent CTA owns a ring of shared-memory stages.  ONE producer thread
+// asks the copy engine for chunk after chunk (a run of consecutive rows whose values, column indices and
+// row pointers are CONTIGUOUS in memory) as stages drain; the consumer warps take rows out of shared
+// memory.  The only long-latency operation left in a consumer is the 256-bit gather of the neighbour's
+// vector entries.
+//
+// Pipeline (second design, profiles/r02_block_rows_barrier.md): every stage has a `full` mbarrier
+// (producer's expect_tx + the copy engine's complete_tx) and an `empty` mbarrier (one arrival per consumer
+// warp).  There is no CTA-wide barrier in the steady state: the first design ended every chunk with
+// __syncthreads and ncu attributed 39 % of all stall samples to it, because a chunk holds fewer rows than
+// the CTA has warps.  Rows are dealt to the consumer warps round-robin ACROSS chunks, so the load is even
+// although a single chunk is not.
 //
 // Two kernels share the machinery:
-//   k_block_rows_staged : the MPET block system, one "node" = NR rows that share their column
-//                         structure (3 displacement rows of a P2 node / A pressure rows of a vertex).
-//   k_spmm_staged       : scalar CSR matrix applied to W-wide vectors with the fused Chebyshev /
-//                         residual epilogue of the AMG V-cycle.
+//   k_block_rows_pipe : the MPET block system, one "node" = NR rows that share their column structure
+//                       (3 displacement rows of a P2 node / A pressure rows of a vertex).
+//   k_spmm_pipe       : scalar CSR matrix applied to W-wide vectors with the fused Chebyshev / residual
+//                       epilogue of the AMG V-cycle.
 #include "ctx.h"
 #include "layout.cuh"
 #include "staged.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -33,6 +41,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -54,90 +65,112 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-constexpr int kStages = 2;     // measured: 3 stages of smaller chunks are slower (per-chunk barrier cost)
-constexpr int kThreads = 256;           // scalar SpMM
-constexpr int kBlkThreads = 512;        // block rows: 16 warps per CTA, 2 CTAs per SM
-constexpr int kWarps = kBlkThreads / 32;
+// ------------------------------------------------------------------------------- configurations
+// THREADS = 32 * (consumer warps + 1 producer warp); MINB = CTAs per SM the shared-memory ring allows.
+template <int THREADS, int STAGES, int CAPV, int MINB>
+struct BlkCfg {
+    static constexpr int kThreads = THREADS, kStages = STAGES, kCapV = CAPV, kMinBlocks = MINB;
+    static constexpr int kConsumers = THREADS / 32 - 1;
+};
+template <int THREADS, int STAGES, int CAP, int ROWS, int MINB>
+struct SpmCfg {
+    static constexpr int kThreads = THREADS, kStages = STAGES, kCap = CAP, kRows = ROWS, kMinBlocks = MINB;
+    static constexpr int kConsumers = THREADS / 32 - 1;
+};
+
+constexpr int kNnMax = 64;      // nodes per block chunk (row-pointer slice)
+
+// values per row group of one block stage when the node has NR rows: the stage keeps NR * capv doubles
+constexpr int blk_capv(int cfg_capv, int nr) { return nr <= 3 ? cfg_capv : ((cfg_capv * 3 / nr) & ~1); }
+constexpr int blk_capc(int capv) { return (capv / 3 + 3) & ~3; }
 
 // ------------------------------------------------------------------------------- block rows
-// shared-memory stage of k_block_rows_staged
-template <int NR>
+template <int NR, int CAPV>
 struct BlockStage {
-    double vals[NR][BLK_CAPV + 2];
-    int32_t colA[BLK_CAPA + 8];
-    int32_t colB[BLK_CAPB + 8];
-    int32_t rpA[BLK_NNMAX + 8];
-    int32_t rpB[BLK_NNMAX + 8];
+    static constexpr int kCapC = blk_capc(CAPV);
+    double vals[NR][CAPV + 2];
+    int32_t colA[kCapC + 8];
+    int32_t colB[kCapC + 8];
+    int32_t rpA[kNnMax + 8];
+    int32_t rpB[kNnMax + 8];
 };
 
 struct GroupBase { int64_t v[MPET_MAX_NETWORKS]; };
 
+template <int NR, class CFG>
+constexpr size_t blk_smem_bytes() {
+    return CFG::kStages * sizeof(BlockStage<NR, blk_capv(CFG::kCapV, NR)>) + 2 * CFG::kStages * sizeof(uint64_t) +
+           CFG::kStages * sizeof(BlockChunk);
+}
+
 // NR rows per node, NA scalar (pressure) column blocks.  U_OUT: rows are the displacement of a P2 node
 // (output = one padded 256-bit store), else the pressures of a vertex (NR scalar stores, stride nv).
-template <int NR, int NA, bool U_OUT>
-__global__ void __launch_bounds__(kBlkThreads, 2)
-k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase gbase,
-                    const int32_t* __restrict__ rpA, const int32_t* __restrict__ colA,
-                    const int32_t* __restrict__ rpB, const int32_t* __restrict__ colB,
-                    const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                    int64_t n2, int64_t nv, const uint8_t* __restrict__ mask, const int* __restrict__ done) {
+template <int NR, int NA, bool U_OUT, class CFG>
+__global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks)
+k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase gbase,
+                  const int32_t* __restrict__ rpA, const int32_t* __restrict__ colA,
+                  const int32_t* __restrict__ rpB, const int32_t* __restrict__ colB,
+                  const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                  int64_t n2, int64_t nv, const uint8_t* __restrict__ mask, const int* __restrict__ done) {
     if (done && *done) return;
+    constexpr int kStages = CFG::kStages, NCW = CFG::kConsumers;
+    using Stage = BlockStage<NR, blk_capv(CFG::kCapV, NR)>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BlockStage<NR>* stage = reinterpret_cast<BlockStage<NR>*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(BlockStage<NR>));
-    BlockChunk* desc = reinterpret_cast<BlockChunk*>(smem_raw + kStages * sizeof(BlockStage<NR>) + 64);
+    Stage* stage = reinterpret_cast<Stage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(Stage));
+    uint64_t* empty = full + kStages;
+    BlockChunk* desc = reinterpret_cast<BlockChunk*>(empty + kStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    auto issue = [&](int ci, int s) {      // called by thread 0 only
-        const BlockChunk c = chunks[ci];
-        desc[s] = c;                        // consumers read the descriptor from shared memory (released by the arrive)
-        BlockStage<NR>& S = stage[s];
-        uint32_t total = 0;
-        // row-pointer slices (aligned to 4 ints)
-        const uint32_t rp_bytes = (uint32_t)c.rp_len * 4u;
-        total += 2 * rp_bytes;
-        // column indices
-        const uint32_t ca_bytes = (uint32_t)c.cA_len * 4u, cb_bytes = (uint32_t)c.cB_len * 4u;
-        total += ca_bytes + cb_bytes;
-        uint32_t vbytes[NR];
-        int64_t vstart[NR];
-#pragma unroll
-        for (int g = 0; g < NR; ++g) {
-            const int64_t s0 = gbase.v[g] + c.v_rel;
-            vstart[g] = s0 & ~(int64_t)1;
-            vbytes[g] = (uint32_t)((((s0 - vstart[g]) + c.v_len + 1) & ~(int64_t)1) * 8);
-            total += vbytes[g];
-        }
-        mbar_expect_tx(&full[s], total);
-        bulk_g2s(S.rpA, rpA + c.rp_off, rp_bytes, &full[s]);
-        bulk_g2s(S.rpB, rpB + c.rp_off, rp_bytes, &full[s]);
-        if (ca_bytes) bulk_g2s(S.colA, colA + c.cA_off, ca_bytes, &full[s]);
-        if (cb_bytes) bulk_g2s(S.colB, colB + c.cB_off, cb_bytes, &full[s]);
-#pragma unroll
-        for (int g = 0; g < NR; ++g) bulk_g2s(S.vals[g], vals + vstart[g], vbytes[g], &full[s]);
-    };
-
     const int first = blockIdx.x, stride = gridDim.x;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages - 1; ++s)
-            if (first + s * stride < nchunks) issue(first + s * stride, s);
-    }
-    int it = 0;
-    for (int ci = first; ci < nchunks; ci += stride, ++it) {
-        const int s = it % kStages;
-        if (threadIdx.x == 0) {
-            const int nxt = ci + (kStages - 1) * stride;
-            if (nxt < nchunks) issue(nxt, (it + kStages - 1) % kStages);
+    const int nmine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer: one thread feeds the copy engine
+        if (lane != 0) return;
+        for (int it = 0; it < nmine; ++it) {
+            const int s = it % kStages;
+            if (it >= kStages) mbar_wait(&empty[s], (uint32_t)((it / kStages - 1) & 1));
+            const BlockChunk c = chunks[first + it * stride];
+            desc[s] = c;                    // consumers read the descriptor from shared memory (released by the arrive)
+            Stage& S = stage[s];
+            const uint32_t rp_bytes = (uint32_t)c.rp_len * 4u;
+            const uint32_t ca_bytes = (uint32_t)c.cA_len * 4u, cb_bytes = (uint32_t)c.cB_len * 4u;
+            uint32_t total = 2 * rp_bytes + ca_bytes + cb_bytes;
+            uint32_t vbytes[NR];
+            int64_t vstart[NR];
+#pragma unroll
+            for (int g = 0; g < NR; ++g) {
+                const int64_t s0 = gbase.v[g] + c.v_rel;
+                vstart[g] = s0 & ~(int64_t)1;
+                vbytes[g] = (uint32_t)((((s0 - vstart[g]) + c.v_len + 1) & ~(int64_t)1) * 8);
+                total += vbytes[g];
+            }
+            mbar_expect_tx(&full[s], total);
+            bulk_g2s(S.rpA, rpA + c.rp_off, rp_bytes, &full[s]);
+            bulk_g2s(S.rpB, rpB + c.rp_off, rp_bytes, &full[s]);
+            if (ca_bytes) bulk_g2s(S.colA, colA + c.cA_off, ca_bytes, &full[s]);
+            if (cb_bytes) bulk_g2s(S.colB, colB + c.cB_off, cb_bytes, &full[s]);
+#pragma unroll
+            for (int g = 0; g < NR; ++g) bulk_g2s(S.vals[g], vals + vstart[g], vbytes[g], &full[s]);
         }
+        return;
+    }
+
+    // ---------------------------------------------------- consumers: one warp per node, dealt round-robin
+    const int cw = warp - 1;
+    int rot = 0;                               // nodes of earlier chunks, modulo NCW
+    for (int it = 0; it < nmine; ++it) {
+        const int s = it % kStages;
         mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
         const BlockChunk c = desc[s];
-        const BlockStage<NR>& S = stage[s];
+        const Stage& S = stage[s];
         const int rsk = c.n0 - c.rp_off;                    // skew of the row-pointer slices
         const int32_t a_base = S.rpA[rsk], b_base = S.rpB[rsk];
         const int ska = a_base - c.cA_off, skb = b_base - c.cB_off;
@@ -145,7 +178,9 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
 #pragma unroll
         for (int g = 0; g < NR; ++g) vsk[g] = (int)((gbase.v[g] + c.v_rel) & 1);
 
-        for (int nl = warp; nl < c.nn; nl += kWarps) {
+        int nl = cw - rot;
+        if (nl < 0) nl += NCW;
+        for (; nl < c.nn; nl += NCW) {
             const int32_t ra = S.rpA[rsk + nl], rb = S.rpB[rsk + nl];
             const int dA = S.rpA[rsk + nl + 1] - ra, dB = S.rpB[rsk + nl + 1] - rb;
             const int eA = ra - a_base + ska, eB = rb - b_base + skb;
@@ -226,74 +261,89 @@ k_block_rows_staged(const BlockChunk* __restrict__ chunks, int nchunks, GroupBas
                 }
             }
         }
-        __syncthreads();     // every warp is done with stage s before thread 0 refills it next iteration
+        rot = (rot + c.nn) % NCW;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);      // this warp is done reading stage s
     }
 }
 
 // ------------------------------------------------------------------------------- scalar SpMM
-template <int W>
+template <int CAP, int ROWS>
 struct SpmmStage {
-    double vals[SPM_CAP + 2];
-    int32_t cols[SPM_CAP + 8];
-    int32_t rp[SPM_ROWS + 8];
+    double vals[CAP + 2];
+    int32_t cols[CAP + 8];
+    int32_t rp[ROWS + 8];
 };
 
 enum { SEPI_RESID = 0, SEPI_CHEB = 1, SEPI_PLAIN = 2 };
 
+template <class CFG>
+constexpr size_t spm_smem_bytes() {
+    return CFG::kStages * sizeof(SpmmStage<CFG::kCap, CFG::kRows>) + 2 * CFG::kStages * sizeof(uint64_t) +
+           CFG::kStages * sizeof(SpmmChunk);
+}
+
 // Row groups of LANES threads; epilogues as in amg.cu (RESID: out = b - Ax; CHEB: Chebyshev step;
 // PLAIN: out = Ax + beta*out).
-template <int W, int LANES, int EPI>
-__global__ void __launch_bounds__(kThreads)
-k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __restrict__ rowptr,
-              const int32_t* __restrict__ cols, const double* __restrict__ vals, const double* __restrict__ x,
-              const double* __restrict__ b, double* __restrict__ out, double* __restrict__ d,
-              const double* __restrict__ dinv, double c1, double c2, const int* __restrict__ done) {
+template <int W, int LANES, int EPI, class CFG>
+__global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks)
+k_spmm_pipe(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __restrict__ rowptr,
+            const int32_t* __restrict__ cols, const double* __restrict__ vals, const double* __restrict__ x,
+            const double* __restrict__ b, double* __restrict__ out, double* __restrict__ d,
+            const double* __restrict__ dinv, double c1, double c2, const int* __restrict__ done) {
     if (done && *done) return;
+    constexpr int kStages = CFG::kStages, NCW = CFG::kConsumers, GPW = 32 / LANES;
+    using Stage = SpmmStage<CFG::kCap, CFG::kRows>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SpmmStage<W>* stage = reinterpret_cast<SpmmStage<W>*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(SpmmStage<W>));
-    SpmmChunk* desc = reinterpret_cast<SpmmChunk*>(smem_raw + kStages * sizeof(SpmmStage<W>) + 64);
-    const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
-    constexpr int kGroups = kThreads / LANES;
+    Stage* stage = reinterpret_cast<Stage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(Stage));
+    uint64_t* empty = full + kStages;
+    SpmmChunk* desc = reinterpret_cast<SpmmChunk*>(empty + kStages);
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int gw = wl / LANES, lane = wl % LANES;          // row group inside the warp, lane inside the group
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    auto issue = [&](int ci, int s) {
-        const SpmmChunk c = chunks[ci];
-        desc[s] = c;
-        SpmmStage<W>& S = stage[s];
-        const uint32_t vb = (uint32_t)c.v_len * 8u, cb = (uint32_t)c.c_len * 4u, rb = (uint32_t)c.rp_len * 4u;
-        mbar_expect_tx(&full[s], vb + cb + rb);
-        bulk_g2s(S.rp, rowptr + c.rp_off, rb, &full[s]);
-        if (vb) bulk_g2s(S.vals, vals + c.v_off, vb, &full[s]);
-        if (cb) bulk_g2s(S.cols, cols + c.c_off, cb, &full[s]);
-    };
-
     const int first = blockIdx.x, stride = gridDim.x;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages - 1; ++s)
-            if (first + s * stride < nchunks) issue(first + s * stride, s);
-    }
-    int it = 0;
-    for (int ci = first; ci < nchunks; ci += stride, ++it) {
-        const int s = it % kStages;
-        if (threadIdx.x == 0) {
-            const int nxt = ci + (kStages - 1) * stride;
-            if (nxt < nchunks) issue(nxt, (it + kStages - 1) % kStages);
+    const int nmine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+
+    if (warp == 0) {
+        if (wl != 0) return;
+        for (int it = 0; it < nmine; ++it) {
+            const int s = it % kStages;
+            if (it >= kStages) mbar_wait(&empty[s], (uint32_t)((it / kStages - 1) & 1));
+            const SpmmChunk c = chunks[first + it * stride];
+            desc[s] = c;
+            Stage& S = stage[s];
+            const uint32_t vb = (uint32_t)c.v_len * 8u, cb = (uint32_t)c.c_len * 4u, rb = (uint32_t)c.rp_len * 4u;
+            mbar_expect_tx(&full[s], vb + cb + rb);
+            bulk_g2s(S.rp, rowptr + c.rp_off, rb, &full[s]);
+            if (vb) bulk_g2s(S.vals, vals + c.v_off, vb, &full[s]);
+            if (cb) bulk_g2s(S.cols, cols + c.c_off, cb, &full[s]);
         }
+        return;
+    }
+
+    const int cw = warp - 1;
+    int rot = 0;                         // row quads (GPW rows) of earlier chunks, modulo NCW
+    for (int it = 0; it < nmine; ++it) {
+        const int s = it % kStages;
         mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
         const SpmmChunk c = desc[s];
-        const SpmmStage<W>& S = stage[s];
+        const Stage& S = stage[s];
         const int rsk = c.r0 - c.rp_off;
         const int32_t e_base = S.rp[rsk];
         const int vsk = e_base - c.v_off, csk = e_base - c.c_off;
+        const int nq = (c.nrows + GPW - 1) / GPW;
+        int q = cw - rot;
+        if (q < 0) q += NCW;
         // warp-uniform trip count: every lane takes part in the shuffles even when its group has no row
-        for (int rbase = 0; rbase < c.nrows; rbase += kGroups) {
-            const int rl = rbase + group;
+        for (; q < nq; q += NCW) {
+            const int rl = q * GPW + gw;
             const bool active = rl < c.nrows;
             const int64_t row = (int64_t)c.r0 + (active ? rl : 0);
             const int32_t e0 = active ? S.rp[rsk + rl] - e_base : 0;
@@ -307,7 +357,7 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
                     if (EPI == SEPI_PLAIN && c1 != 0.0) ex1 = out[row];
                 } else {
                     if (EPI != SEPI_PLAIN) eb4 = ld256(b + 4 * row);
-                    if (EPI == SEPI_CHEB) { edi = dinv[row]; ex4 = ld256(x + 4 * row); if (c1 != 0.0) ed4 = ld256(d + 4 * row); }
+                    if (EPI == SEPI_CHEB) { edi = dinv[row]; ex4 = ld256(x + 4 * row); }   // d is read after the sweep (registers)
                     if (EPI == SEPI_PLAIN && c1 != 0.0) ex4 = ld256(out + 4 * row);
                 }
             }
@@ -353,6 +403,7 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
                             st256(out + 4 * row, res);
                         } else {
                             const double s2 = c2 * edi;
+                            if (c1 != 0.0) ed4 = ld256(d + 4 * row);
                             d4 dn = {s2 * res.x + c1 * ed4.x, s2 * res.y + c1 * ed4.y, s2 * res.z + c1 * ed4.z,
                                      s2 * res.w + c1 * ed4.w};
                             st256(d + 4 * row, dn);
@@ -363,8 +414,40 @@ k_spmm_staged(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* 
                 }
             }
         }
-        __syncthreads();
+        rot = (rot + nq) % NCW;
+        __syncwarp();
+        if (wl == 0) mbar_arrive(&empty[s]);
     }
+}
+
+// ------------------------------------------------------------------------------- configurations in use
+// Measured on B200 (profiles/r02_pipeline_sweep.md); MPET_BLK_CFG / MPET_SPM_CFG select another one
+// at plan-build time (development aid).
+using BlkCfg0 = BlkCfg<512, 4, 960, 2>;
+using BlkCfg1 = BlkCfg<1024, 8, 960, 1>;
+using BlkCfg2 = BlkCfg<512, 3, 1344, 2>;
+using BlkCfg3 = BlkCfg<512, 6, 640, 2>;
+using BlkCfg4 = BlkCfg<1024, 6, 1344, 1>;
+using BlkCfg5 = BlkCfg<384, 4, 960, 2>;
+constexpr int kNumBlkCfg = 6;
+constexpr int kBlkCapV[kNumBlkCfg] = {BlkCfg0::kCapV, BlkCfg1::kCapV, BlkCfg2::kCapV, BlkCfg3::kCapV, BlkCfg4::kCapV,
+                                      BlkCfg5::kCapV};
+
+using SpmCfg0 = SpmCfg<512, 4, 2048, 256, 2>;
+using SpmCfg1 = SpmCfg<1024, 8, 2048, 256, 1>;
+using SpmCfg2 = SpmCfg<256, 4, 1024, 128, 4>;
+using SpmCfg3 = SpmCfg<512, 6, 1344, 192, 2>;
+using SpmCfg4 = SpmCfg<384, 4, 2048, 256, 2>;     // 768 threads per SM: 85 registers, no spills in the W = 4 Chebyshev step
+using SpmCfg5 = SpmCfg<768, 8, 2048, 256, 1>;
+constexpr int kNumSpmCfg = 6;
+constexpr int kSpmCap[kNumSpmCfg] = {2048, 2048, 1024, 1344, 2048, 2048};
+constexpr int kSpmRows[kNumSpmCfg] = {256, 256, 128, 192, 256, 256};
+
+int env_cfg(const char* name, int n, int dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    int v = atoi(e);
+    return (v >= 0 && v < n) ? v : dflt;
 }
 
 template <typename T>
@@ -374,40 +457,56 @@ T* upload_vec(mpet_ctx* ctx, const std::vector<T>& h) {
     return d;
 }
 
-template <int NR, int NA, bool U_OUT>
+template <int NR, int NA, bool U_OUT, class CFG>
 void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
                        const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
                        cudaStream_t st) {
-    const size_t smem = kStages * sizeof(BlockStage<NR>) + 64 + kStages * sizeof(BlockChunk);
-    auto kern = k_block_rows_staged<NR, NA, U_OUT>;
+    constexpr size_t smem = blk_smem_bytes<NR, CFG>();
+    auto kern = k_block_rows_pipe<NR, NA, U_OUT, CFG>;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    int grid = std::min(P.nchunks, 2 * ctx->sm_count);
-    kern<<<grid, kBlkThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x, y,
-                                       ctx->N2, ctx->Nv, mask, done);
+    int grid = std::min(P.nchunks, CFG::kMinBlocks * ctx->sm_count);
+    kern<<<grid, CFG::kThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x,
+                                            y, ctx->N2, ctx->Nv, mask, done);
     LAUNCH_CHECK(ctx);
 }
 
-template <int NA>
+template <int NA, class CFG>
 void block_rows_all(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done, cudaStream_t st) {
     // value runs: row (k, a) starts at k*T + 3*rp22[a] + NA*rp21[a]; row (i, v) at 3*T + i*Tp + 3*rp12[v] + NA*rp11[v]
     const int64_t T = 3 * ctx->g22.nnz + (int64_t)NA * ctx->g21.nnz;
     const int64_t Tp = 3 * ctx->g12.nnz + (int64_t)NA * ctx->g11.nnz;
     GroupBase gu, gp;
     for (int k = 0; k < MPET_MAX_NETWORKS; ++k) { gu.v[k] = (int64_t)k * T; gp.v[k] = 3 * T + (int64_t)k * Tp; }
-    launch_block_rows<3, NA, true>(ctx, ctx->plan_u, gu, ctx->g22, ctx->g21, x, y, mask, done, st);
+    launch_block_rows<3, NA, true, CFG>(ctx, ctx->plan_u, gu, ctx->g22, ctx->g21, x, y, mask, done, st);
     if (NA > 0)
-        launch_block_rows<(NA > 0 ? NA : 1), NA, false>(ctx, ctx->plan_p, gp, ctx->g12, ctx->g11, x, y, mask, done, st);
+        launch_block_rows<(NA > 0 ? NA : 1), NA, false, CFG>(ctx, ctx->plan_p, gp, ctx->g12, ctx->g11, x, y, mask, done, st);
+}
+
+template <class CFG>
+bool block_rows_cfg(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done, cudaStream_t st) {
+    switch (ctx->A) {
+        case 0: block_rows_all<0, CFG>(ctx, x, y, mask, done, st); break;
+        case 1: block_rows_all<1, CFG>(ctx, x, y, mask, done, st); break;
+        case 2: block_rows_all<2, CFG>(ctx, x, y, mask, done, st); break;
+        case 3: block_rows_all<3, CFG>(ctx, x, y, mask, done, st); break;
+        case 4: block_rows_all<4, CFG>(ctx, x, y, mask, done, st); break;
+        case 5: block_rows_all<5, CFG>(ctx, x, y, mask, done, st); break;
+        default: return false;
+    }
+    return true;
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------- host: plans
 // Greedy chunking of consecutive nodes so that every staged array fits its shared-memory slot.
-static bool build_block_plan(mpet_ctx* ctx, const NodeGraph& gA, const NodeGraph& gB, int NA, int NR, BlockPlan& plan) {
+static bool build_block_plan(mpet_ctx* ctx, const NodeGraph& gA, const NodeGraph& gB, int NA, int NR, int cfg,
+                             BlockPlan& plan) {
+    const int capV = blk_capv(kBlkCapV[cfg], NR), capC = blk_capc(capV);
     const int64_t n = gA.nrows;
     std::vector<int32_t> rpA(n + 1), rpB(n + 1);
     CUDA_CHECK(cudaMemcpy(rpA.data(), gA.rowptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
@@ -419,8 +518,9 @@ static bool build_block_plan(mpet_ctx* ctx, const NodeGraph& gA, const NodeGraph
         const int rp_off = (int)(a0 & ~(int64_t)3);
         while (a1 < n) {
             const int64_t vlen = 3 * (int64_t)(rpA[a1 + 1] - rpA[a0]) + (int64_t)NA * (rpB[a1 + 1] - rpB[a0]);
-            const int64_t la = rpA[a1 + 1] - rpA[a0], lb = rpB[a1 + 1] - rpB[a0];
-            if (vlen > BLK_CAPV || la > BLK_CAPA || lb > BLK_CAPB || (a1 + 1 - rp_off) + 1 > BLK_NNMAX) break;
+            // column slices start at the aligned-down offset: up to 3 leading pad entries
+            const int64_t la = rpA[a1 + 1] - (rpA[a0] & ~3), lb = rpB[a1 + 1] - (rpB[a0] & ~3);
+            if (vlen > capV || la > capC || lb > capC || (a1 + 1 - rp_off) + 1 > kNnMax) break;
             ++a1;
         }
         if (a1 == a0) return false;      // a single node does not fit: caller falls back
@@ -439,41 +539,45 @@ static bool build_block_plan(mpet_ctx* ctx, const NodeGraph& gA, const NodeGraph
         chunks.push_back(c);
         a0 = a1;
     }
-    (void)NR;
     plan.nchunks = (int)chunks.size();
     plan.chunks = upload_vec(ctx, chunks);
+    plan.cfg = cfg;
     return true;
 }
 
 void staged_build_block_plans(mpet_ctx* ctx) {
-    ctx->staged_ok = build_block_plan(ctx, ctx->g22, ctx->g21, ctx->A, 3, ctx->plan_u);
+    const int cfg = env_cfg("MPET_BLK_CFG", kNumBlkCfg, 0);
+    ctx->staged_ok = ctx->A <= 5 && build_block_plan(ctx, ctx->g22, ctx->g21, ctx->A, 3, cfg, ctx->plan_u);
     if (ctx->staged_ok && ctx->A > 0)
-        ctx->staged_ok = build_block_plan(ctx, ctx->g12, ctx->g11, ctx->A, ctx->A, ctx->plan_p);
+        ctx->staged_ok = build_block_plan(ctx, ctx->g12, ctx->g11, ctx->A, ctx->A, cfg, ctx->plan_p);
 }
 
 bool staged_block_spmv(mpet_ctx* ctx, const double* x, double* y, const uint8_t* mask, const int* done,
                        cudaStream_t st) {
     if (!ctx->staged_ok) return false;
-    switch (ctx->A) {
-        case 0: block_rows_all<0>(ctx, x, y, mask, done, st); break;
-        case 1: block_rows_all<1>(ctx, x, y, mask, done, st); break;
-        case 2: block_rows_all<2>(ctx, x, y, mask, done, st); break;
-        case 3: block_rows_all<3>(ctx, x, y, mask, done, st); break;
-        case 4: block_rows_all<4>(ctx, x, y, mask, done, st); break;
+    switch (ctx->plan_u.cfg) {
+        case 0: return block_rows_cfg<BlkCfg0>(ctx, x, y, mask, done, st);
+        case 1: return block_rows_cfg<BlkCfg1>(ctx, x, y, mask, done, st);
+        case 2: return block_rows_cfg<BlkCfg2>(ctx, x, y, mask, done, st);
+        case 3: return block_rows_cfg<BlkCfg3>(ctx, x, y, mask, done, st);
+        case 4: return block_rows_cfg<BlkCfg4>(ctx, x, y, mask, done, st);
+        case 5: return block_rows_cfg<BlkCfg5>(ctx, x, y, mask, done, st);
         default: return false;
     }
-    return true;
 }
 
-// scalar CSR: chunks of consecutive rows with at most SPM_CAP entries / SPM_ROWS rows
+// scalar CSR: chunks of consecutive rows with at most cap entries / rows rows
 bool staged_build_spmm_plan(mpet_ctx* ctx, const std::vector<int32_t>& rp, SpmmPlan& plan) {
+    const int cfg = env_cfg("MPET_SPM_CFG", kNumSpmCfg, 0);
+    const int cap = kSpmCap[cfg], rows = kSpmRows[cfg];
     const int64_t n = (int64_t)rp.size() - 1;
     std::vector<SpmmChunk> chunks;
     int64_t r0 = 0;
     while (r0 < n) {
         const int rp_off = (int)(r0 & ~(int64_t)3);
+        const int32_t c_off = rp[r0] & ~3;          // aligned-down start of the staged slices (up to 3 pad entries)
         int64_t r1 = r0;
-        while (r1 < n && (rp[r1 + 1] - rp[r0]) <= SPM_CAP && ((r1 + 1 - rp_off) + 1) <= SPM_ROWS) ++r1;
+        while (r1 < n && (rp[r1 + 1] - c_off) <= cap && ((r1 + 1 - rp_off) + 1) <= rows) ++r1;
         if (r1 == r0) return false;
         SpmmChunk c;
         c.r0 = (int32_t)r0;
@@ -482,53 +586,68 @@ bool staged_build_spmm_plan(mpet_ctx* ctx, const std::vector<int32_t>& rp, SpmmP
         c.rp_len = (int32_t)((((r1 + 1) - rp_off) + 3) & ~(int64_t)3);
         c.v_off = rp[r0] & ~1;
         c.v_len = ((rp[r1] - c.v_off) + 1) & ~1;
-        c.c_off = rp[r0] & ~3;
+        c.c_off = c_off;
         c.c_len = ((rp[r1] - c.c_off) + 3) & ~3;
         chunks.push_back(c);
         r0 = r1;
     }
     plan.nchunks = (int)chunks.size();
     plan.chunks = upload_vec(ctx, chunks);
+    plan.cfg = cfg;
     return true;
 }
 
-template <int W, int LANES, int EPI>
-static void launch_spmm_staged(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
-                               double* out, double* d, const double* dinv, double c1, double c2, const int* done,
-                               cudaStream_t st) {
-    const size_t smem = kStages * sizeof(SpmmStage<W>) + 64 + kStages * sizeof(SpmmChunk);
-    auto kern = k_spmm_staged<W, LANES, EPI>;
+template <int W, int LANES, int EPI, class CFG>
+static void launch_spmm_pipe(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
+                             double* out, double* d, const double* dinv, double c1, double c2, const int* done,
+                             cudaStream_t st) {
+    constexpr size_t smem = spm_smem_bytes<CFG>();
+    auto kern = k_spmm_pipe<W, LANES, EPI, CFG>;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    int grid = std::min(P.nchunks, 4 * ctx->sm_count);
-    kern<<<grid, kThreads, smem, st>>>(P.chunks, P.nchunks, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
+    int grid = std::min(P.nchunks, CFG::kMinBlocks * ctx->sm_count);
+    kern<<<grid, CFG::kThreads, smem, st>>>(P.chunks, P.nchunks, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
     LAUNCH_CHECK(ctx);
 }
 
-template <int W, int EPI>
-static void spmm_staged_lanes(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
-                              double* out, double* d, const double* dinv, double c1, double c2, const int* done,
-                              cudaStream_t st) {
+template <int W, int EPI, class CFG>
+static void spmm_pipe_lanes(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
+                            double* out, double* d, const double* dinv, double c1, double c2, const int* done,
+                            cudaStream_t st) {
     const double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
-    if (mean > 40) launch_spmm_staged<W, 32, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    else if (mean > 32) launch_spmm_staged<W, 16, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    else if (mean > 5) launch_spmm_staged<W, 8, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    else launch_spmm_staged<W, 4, EPI>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    if (mean > 40) launch_spmm_pipe<W, 32, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    else if (mean > 32) launch_spmm_pipe<W, 16, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    else if (mean > 5) launch_spmm_pipe<W, 8, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    else launch_spmm_pipe<W, 4, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+}
+
+template <class CFG>
+static void spmm_pipe_cfg(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr& M, const double* x,
+                          const double* b, double* out, double* d, const double* dinv, double c1, double c2,
+                          const int* done, cudaStream_t st) {
+    if (W == 4) {
+        if (epi == 0) spmm_pipe_lanes<4, SEPI_RESID, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else if (epi == 1) spmm_pipe_lanes<4, SEPI_CHEB, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else spmm_pipe_lanes<4, SEPI_PLAIN, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    } else {
+        if (epi == 0) spmm_pipe_lanes<1, SEPI_RESID, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else if (epi == 1) spmm_pipe_lanes<1, SEPI_CHEB, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+        else spmm_pipe_lanes<1, SEPI_PLAIN, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    }
 }
 
 // epi: 0 = residual, 1 = Chebyshev step, 2 = plain (out = M x + c1 * out)
 void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
                  double* out, double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
-    if (W == 4) {
-        if (epi == 0) spmm_staged_lanes<4, SEPI_RESID>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-        else if (epi == 1) spmm_staged_lanes<4, SEPI_CHEB>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-        else spmm_staged_lanes<4, SEPI_PLAIN>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    } else {
-        if (epi == 0) spmm_staged_lanes<1, SEPI_RESID>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-        else if (epi == 1) spmm_staged_lanes<1, SEPI_CHEB>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-        else spmm_staged_lanes<1, SEPI_PLAIN>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    switch (P.cfg) {
+        case 1: spmm_pipe_cfg<SpmCfg1>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 2: spmm_pipe_cfg<SpmCfg2>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 3: spmm_pipe_cfg<SpmCfg3>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 4: spmm_pipe_cfg<SpmCfg4>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 5: spmm_pipe_cfg<SpmCfg5>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        default: spmm_pipe_cfg<SpmCfg0>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
     }
 }

@@ -3,14 +3,6 @@
 #include <stdint.h>
 #include <vector>
 
-// capacities of one shared-memory stage
-#define BLK_CAPV 1344     // values per row group
-#define BLK_CAPA 448      // primary (vector-valued) column indices
-#define BLK_CAPB 448      // secondary (scalar) column indices
-#define BLK_NNMAX 128     // nodes
-#define SPM_CAP 2048      // entries
-#define SPM_ROWS 256      // rows
-
 struct BlockChunk {       // a run of consecutive nodes of the block system
     int32_t n0, nn;                 // first node, number of nodes
     int32_t rp_off, rp_len;         // 16-byte aligned slice of the node row pointers
@@ -27,5 +19,6 @@ struct SpmmChunk {        // a run of consecutive rows of a scalar CSR matrix
     int32_t c_off, c_len;
 };
 
-struct BlockPlan { BlockChunk* chunks = nullptr; int nchunks = 0; };
-struct SpmmPlan { SpmmChunk* chunks = nullptr; int nchunks = 0; };
+// cfg = index of the pipeline configuration (threads / stages / stage capacity) the plan was cut for
+struct BlockPlan { BlockChunk* chunks = nullptr; int nchunks = 0; int cfg = 0; };
+struct SpmmPlan { SpmmChunk* chunks = nullptr; int nchunks = 0; int cfg = 0; };
