@@ -181,12 +181,17 @@ def build_oracle_problem(config, n):
 
 
 def run_cpu(config, n, rtol, steps, warmup, maxit):
-    """(seconds per step, dofs, iterations) of the oracle's step on the host."""
+    """(seconds per step, dofs, iterations, threads) of the oracle's step on the host: numpy assembly, then
+    MINRES + block AMG with every sparse product on all host cores (oracle/omp.py, OpenMP row loops)."""
     import numpy as np
     from oracle.krylov import minres, BlockAMG
+    from oracle import omp
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(1, user_api="blas")       # numpy's BLAS pool would fight the OpenMP row loops for the cores
+    threads = omp.num_threads()
     o = build_oracle_problem(config, n)
     dofs, _ = o.dirichlet(o.t)
-    M = BlockAMG(o, dofs)                       # hierarchy set-up is outside the step on both arms
+    M = omp.parallelise(BlockAMG(o, dofs))      # hierarchy set-up is outside the step on both arms
     B = o.assemble_prev_operator()
     mask = np.zeros(o.space.N, dtype=bool)
     mask[dofs] = True
@@ -198,14 +203,14 @@ def run_cpu(config, n, rtol, steps, warmup, maxit):
         b, _, vals = o.rhs(o.t, B)
         x0 = x.copy()
         x0[dofs] = vals
-        x, info = minres(A, b, x0, M, mask=mask, rtol=rtol, maxit=maxit)
+        x, info = minres(omp.OmpCsr(A), b, x0, M, mask=mask, rtol=rtol, maxit=maxit)
         t1 = time.perf_counter()
         o.t += o.dt
         o.up_ = x.copy()
         if k >= warmup:
             times.append(t1 - t0)
             iters.append(info["niter"])
-    return sum(times) / len(times), o.space.N, iters
+    return sum(times) / len(times), o.space.N, iters, threads
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -218,9 +223,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        sec, dofs, iters = run_cpu(args.config, args.cpu_n, args.rtol, max(1, args.steps), max(0, min(args.warmup, 1)),
-                                   args.maxit)
+        sec, dofs, iters, threads = run_cpu(args.config, args.cpu_n, args.rtol, max(1, args.steps),
+                                            max(0, min(args.warmup, 1)), args.maxit)
         val = dofs / sec
         sample = "%s family at n=%d (%d dofs), %d step(s), MINRES its %s" % (args.config, args.cpu_n, dofs,
                                                                              len(iters), iters)
@@ -228,10 +232,9 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s: %s" % (args.config, sample), "rtol": args.rtol,
-                           "note": "CPU restatement (numpy/scipy oracle) of the reference path; DOLFIN/PETSc "
-                                   "are not installable offline"},
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                                 "host_threads_available": threads},
+                           "note": "CPU restatement (numpy assembly + OpenMP CSR products, oracle/) of the reference "
+                                   "path; DOLFIN/PETSc are not installable offline"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -258,12 +261,13 @@ def main():
     n = args.n or cfg["n"]
     partition = None
     if world > 1:
-        # weak scaling: the box grows along z, every rank owns an n^3 slab (+ one ghost cell layer per side)
+        # weak scaling on the REFINED CUBE of BASELINE.json configs[4]: the domain stays the cube, the mesh is
+        # refined isotropically to n * world^(1/3) cells per edge (so every rank keeps ~n^3 cubes of 6 tets),
+        # and is cut into `world` z-slabs (+ one ghost cell layer per cut)
         from waterscapes_b200.parallel import box_slab, Partition
-        if args.config in ("cfg1", "cfg2"):
-            mesh = box_slab((0.0, 0.0, 0.0), (1.0, 1.0, float(world)), n, n, n * world, rank, world)
-        else:
-            mesh = box_slab((0.0, 0.0, 0.0), (120.0, 120.0, 120.0 * world), n, n, n * world, rank, world)
+        ng = int(round(n * world ** (1.0 / 3.0)))
+        L = 1.0 if args.config in ("cfg1", "cfg2") else 120.0
+        mesh = box_slab((0.0, 0.0, 0.0), (L, L, L), ng, ng, ng, rank, world)
         problem, sp, init = make_problem(args.config, n, mesh=mesh)
         partition = Partition(rank, world)
     else:
@@ -363,7 +367,7 @@ def main():
                                    "step = assemble A + b, Dirichlet, MINRES+block-AMG to rtol %g"
                                    % (args.config, S["A"], n, S["Nc"], N, S["nnz"], args.rtol),
                        "dofs_per_gpu": N, "nnz_per_gpu": S["nnz"], "rtol": args.rtol, "krylov_iterations": iters,
-                       "parallelism": "1 GPU" if world == 1 else "%d z-slabs (cells + 1 ghost layer), NCCL halo exchange + all-reduced dots, additive-Schwarz V-cycles" % world,
+                       "parallelism": "1 GPU" if world == 1 else "cube refined to %d^3 cubes, %d z-slabs (own cells + 1 ghost layer), NCCL halo exchange + all-reduced dots, distributed V-cycles" % (int(round(n * world ** (1.0 / 3.0))), world),
                        "total_dofs": total_dofs,
                        "l2": "inputs (%.1f GB matrix) larger than the 126 MB L2" % (12 * S["nnz"] / 1e9),
                        "amg_setup_s_excluded": round(setup_s, 2)},
@@ -373,8 +377,8 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, dofs, cit = run_cpu(args.config, args.cpu_n, args.rtol, 1, 0, args.maxit)
-        line["cpu_baseline"] = {"value": dofs / sec, "unit": UNIT, "cores": 1, "kind": "port",
+        sec, dofs, cit, threads = run_cpu(args.config, args.cpu_n, args.rtol, 1, 0, args.maxit)
+        line["cpu_baseline"] = {"value": dofs / sec, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%s family at n=%d (%d dofs), 1 step, %s MINRES iterations, %.1f s"
                                           % (args.config, args.cpu_n, dofs, cit, sec)}
     if rank == 0:

@@ -60,6 +60,13 @@ int mpet_get_pattern(mpet_ctx* ctx, int64_t* rowptr_dev, int32_t* cols_dev, void
 int mpet_set_params(mpet_ctx* ctx, double E, double nu, const double* alpha_host,
                     const double* K_host, const double* S_host, const double* c_host,
                     double dt, double theta);
+/* Total-pressure formulation (mpettotalpressuresolver.py:267-283: unknowns u, p0 = total pressure,
+ * p_1..p_J): the context must have been created with n_networks = J + 1 P1 fields (field 0 is p0);
+ * alpha, K, c: host f64[J]; S: host f64[J*J].  Every other entry point (assembly, right-hand side,
+ * preconditioner, Krylov solve) is shared with the standard formulation. */
+int mpet_set_params_total_pressure(mpet_ctx* ctx, double E, double nu, const double* alpha_host,
+                                   const double* K_host, const double* S_host, const double* c_host,
+                                   double dt, double theta);
 
 /* ---- matrix assembly ---------------------------------------------------------------------------
  * mpet_assemble_lhs  : A = assemble(a)                       (mpetsolver.py:335,412,496; form :196-201,260)

@@ -263,7 +263,7 @@ class BlockAMG:
         assert o.d == 3 and sp_.nreal == 0 and sp_.perm is None
         from .mpet import convert_to_mu_lmbda
         mu, _ = convert_to_mu_lmbda(o.E, o.nu)
-        N2, Nv, A = sp_.N2, sp_.Nv, o.A
+        N2, Nv, A = sp_.N2, sp_.Nv, o.nfields
         mask = np.zeros(sp_.N, dtype=bool)
         mask[dirichlet_dofs] = True
         for k in (1, 2):

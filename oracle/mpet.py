@@ -98,6 +98,8 @@ ZERO = Coef(value=0.0)
 class MPETOracle:
     """Oracle twin of ``MPETProblem`` + ``MPETSolver`` (standard formulation)."""
 
+    P_SHIFT = 0      # P1 field index of network i is i + P_SHIFT (the total-pressure twin puts p0 first)
+
     def __init__(self, mesh, params, dt=0.1, theta=1.0, t=0.0, T=1.0,
                  u_has_nullspace=False, p_has_nullspace=None, perm=None):
         self.mesh = mesh
@@ -115,7 +117,8 @@ class MPETOracle:
         self.p_has_nullspace = list(p_has_nullspace) if p_has_nullspace is not None else [False] * A
         self.Z = self.rigid_motions() if self.u_has_nullspace else []
         nreal = len(self.Z) + sum(self.p_has_nullspace)
-        self.space = MixedSpace(mesh, A, nreal=nreal, perm=perm)
+        self.nfields = A + self.P_SHIFT                       # P1 fields of the mixed space
+        self.space = MixedSpace(mesh, self.nfields, nreal=nreal, perm=perm)
         # data (mpetproblem.py:141-149 defaults)
         zero_vec = Coef(value=(0.0,) * d)
         self.f, self.s, self.u_bar = zero_vec, zero_vec, zero_vec
@@ -365,7 +368,7 @@ class MPETOracle:
             d = self.d
             Mref = (np.ones((d, d)) + np.eye(d)) / (d * (d + 1))   # P1 facet mass / measure
             fv = self.facets["vertices"][sel]
-            dofs = self.space._p(d * self.space.N2 + i * self.space.Nv + fv)
+            dofs = self.space._p(d * self.space.N2 + (i + self.P_SHIFT) * self.space.Nv + fv)
             vals = -self.dt * self.theta * beta * meas[:, None, None] * Mref[None]
             rows = np.repeat(dofs[:, :, None], d, axis=2)
             cols = np.repeat(dofs[:, None, :], d, axis=1)
@@ -389,7 +392,7 @@ class MPETOracle:
         for i, flag in enumerate(self.p_has_nullspace):
             if not flag:
                 continue
-            vec = self._cell_load(Coef(value=1.0), 0.0, ("p", i))
+            vec = self._cell_load(Coef(value=1.0), 0.0, ("p", i + self.P_SHIFT))
             nz = np.nonzero(vec)[0]
             rows += [np.full(nz.size, r), nz]
             cols += [nz, np.full(nz.size, r)]
@@ -472,15 +475,16 @@ class MPETOracle:
     def assemble_L1(self, i, t):
         """``assemble(L1[i])`` at time t (mpetsolver.py:249-254,440-442)."""
         dt, th = self.dt, self.theta
-        b = dt * self._cell_load(self.g[i], t, ("p", i))
+        f = i + self.P_SHIFT
+        b = dt * self._cell_load(self.g[i], t, ("p", f))
         sel = np.nonzero(self.continuity_markers[i] == NEUMANN_MARKER)[0]
-        b += dt * self._facet_load(self.I[i], t, ("p", i), sel)
+        b += dt * self._facet_load(self.I[i], t, ("p", f), sel)
         sel = np.nonzero(self.continuity_markers[i] == ROBIN_MARKER)[0]
         if sel.size and not self.beta[i].is_zero(t):
             beta = float(self.beta[i].const(t))
-            b -= dt * beta * self._facet_load(self.p_robin[i], t, ("p", i), sel)
+            b -= dt * beta * self._facet_load(self.p_robin[i], t, ("p", f), sel)
             if th != 1.0:
-                pdofs = self.space.p_dofs(i)
+                pdofs = self.space.p_dofs(f)
                 pprev = self.up_[pdofs]
                 # (1-theta) * beta * p_prev is P1: integrate exactly with the facet mass
                 fv = self.facets["vertices"][sel]
@@ -518,7 +522,7 @@ class MPETOracle:
             sel = np.nonzero(self.continuity_markers[i] == DIRICHLET_MARKER)[0]
             if sel.size:
                 verts = np.unique(self.facets["vertices"][sel])
-                dofs.append(sp_._p(d * sp_.N2 + i * sp_.Nv + verts))
+                dofs.append(sp_._p(d * sp_.N2 + (i + self.P_SHIFT) * sp_.Nv + verts))
                 vals.append(self.p_bar[i].at_points(self.mesh.coords[verts], t))
         if not dofs:
             return np.zeros(0, dtype=np.int64), np.zeros(0)
@@ -597,12 +601,13 @@ class MPETOracle:
         up = self.up if up is None else up
         sp_ = self.space
         u = np.stack([up[sp_.u_dofs(k)] for k in range(self.d)], axis=1)
-        p = [up[sp_.p_dofs(i)] for i in range(self.A)]
+        p = [up[sp_.p_dofs(i)] for i in range(self.nfields)]
         return u, p
 
-    def error_norms(self, up, u_exact, p_exact, t, qdeg=8, grad_u=None, grad_p=None):
+    def error_norms(self, up, u_exact, p_exact, t, qdeg=8, grad_u=None, grad_p=None, fields=None):
         """L2 (and H1 when exact gradients are given) errors, high-order quadrature
-        (the reference uses ``errornorm(..., degree_rise=5)``)."""
+        (the reference uses ``errornorm(..., degree_rise=5)``).  ``fields``: P1 field index of every
+        entry of ``p_exact`` (default 0, 1, ...)."""
         d = self.d
         sp_ = self.space
         pts, wts = simplex_quadrature(d, qdeg)
@@ -623,7 +628,9 @@ class MPETOracle:
             gue = grad_u(xq.reshape(-1, d), t).reshape(guh.shape)
             out["u_H1"] = np.sqrt(out["u_L2"] ** 2 + np.einsum("cq,cqkm,cqkm->", w, guh - gue, guh - gue))
         out["p_L2"], out["p_H1"] = [], []
-        for i in range(self.A):
+        fields = list(range(len(p_exact))) if fields is None else fields
+        p = [p[f] for f in fields]
+        for i in range(len(p_exact)):
             ph = np.einsum("qm,cm->cq", N1, p[i][self.mesh.cells])
             pe = p_exact[i](xq.reshape(-1, d), t).reshape(ph.shape)
             l2 = np.sqrt(np.einsum("cq,cq,cq->", w, ph - pe, ph - pe))
@@ -664,3 +671,104 @@ def _solve_iterative(self, rtol=1e-5, atol=1e-50, maxit=10000, monitor=None, rea
 
 
 MPETOracle.solve_iterative = _solve_iterative
+
+
+# ---------------------------------------------------------------------------------- total pressure
+class MPETTotalPressureOracle(MPETOracle):
+    """Oracle twin of ``MPETTotalPressureSolver`` (mpettotalpressuresolver.py:164-328): unknowns
+    (u, p0, p_1..p_J) with p0 the total pressure; P1 field 0 is p0, field i + 1 is network i.
+
+    F (mpettotalpressuresolver.py:267-274), split with lhs/rhs:
+      2 mu (eps(u), eps(v)) + (p0, div v)
+      + (div u, w0) - 1/lambda (sum_i alpha_i p_i + p0, w0)
+      + sum_i [ -c_i (p_i - p_i^-, w_i) - alpha_i/lambda (p0 - p0^- + sum_j alpha_j (p_j - p_j^-), w_i)
+                - dt K_i (grad pm_i, grad w_i) - dt sum_j S_ij (pm_i - pm_j, w_i) ],   pm = theta p + (1-theta) p^-.
+    The time loop (rhs groups and their times) is the standard one; see ``MPETOracle.rhs``."""
+
+    P_SHIFT = 1
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        assert not self.u_has_nullspace and not any(self.p_has_nullspace), \
+            "nullspace multipliers are not restated for the total-pressure twin"
+
+    def element_matrix_lhs(self, cells):
+        """``a = lhs(F)`` per cell (mpettotalpressuresolver.py:267-274)."""
+        d, J = self.d, self.A
+        sp_ = self.space
+        n2, n1, nloc = sp_.n2, sp_.n1, sp_.nloc
+        mu, lmbda = convert_to_mu_lmbda(self.E, self.nu)
+        dt, th = self.dt, self.theta
+        G, D, M, Lp = self.element_blocks(cells)
+        Ae = np.zeros((len(cells), nloc, nloc))
+        trG = np.einsum("cabmm->cab", G)
+        for k in range(d):
+            for l in range(d):
+                blk = mu * G[:, :, :, l, k]               # 2 mu eps:eps = mu (grad u:grad v + grad u^T:grad v)
+                if k == l:
+                    blk = blk + mu * trG
+                Ae[:, k * n2:(k + 1) * n2, l * n2:(l + 1) * n2] = blk
+        p0 = d * n2
+        for k in range(d):
+            Ae[:, k * n2:(k + 1) * n2, p0:p0 + n1] = D[:, :, :, k]                       # + p0 div v
+            Ae[:, p0:p0 + n1, k * n2:(k + 1) * n2] = np.swapaxes(D[:, :, :, k], 1, 2)    # + div u w0
+        Ae[:, p0:p0 + n1, p0:p0 + n1] = -(1.0 / lmbda) * M
+        for i in range(J):
+            pi = d * n2 + (i + 1) * n1
+            Ae[:, p0:p0 + n1, pi:pi + n1] = -(self.alpha[i] / lmbda) * M                 # row w0
+            Ae[:, pi:pi + n1, p0:p0 + n1] = -(self.alpha[i] / lmbda) * M                 # row w_i, col p0
+            offsum = sum(self.S[i, j] for j in range(J) if j != i)
+            for j in range(J):
+                pj = d * n2 + (j + 1) * n1
+                blk = -(self.alpha[i] * self.alpha[j] / lmbda) * M
+                if j == i:
+                    blk = blk - self.c[i] * M - dt * th * self.K[i] * Lp - dt * th * offsum * M
+                else:
+                    blk = blk + dt * th * self.S[i, j] * M
+                Ae[:, pi:pi + n1, pj:pj + n1] = blk
+        return Ae
+
+    def element_matrix_prev(self, cells):
+        """Operator of ``L = rhs(F)`` on the previous state (rows w_i only; w0 and v rows are zero)."""
+        d, J = self.d, self.A
+        sp_ = self.space
+        n2, n1, nloc = sp_.n2, sp_.n1, sp_.nloc
+        _, lmbda = convert_to_mu_lmbda(self.E, self.nu)
+        dt, th = self.dt, self.theta
+        G, D, M, Lp = self.element_blocks(cells)
+        Be = np.zeros((len(cells), nloc, nloc))
+        p0 = d * n2
+        for i in range(J):
+            pi = d * n2 + (i + 1) * n1
+            Be[:, pi:pi + n1, p0:p0 + n1] = -(self.alpha[i] / lmbda) * M
+            offsum = sum(self.S[i, j] for j in range(J) if j != i)
+            for j in range(J):
+                pj = d * n2 + (j + 1) * n1
+                blk = -(self.alpha[i] * self.alpha[j] / lmbda) * M
+                if j == i:
+                    blk = blk - self.c[i] * M + dt * (1 - th) * self.K[i] * Lp + dt * (1 - th) * offsum * M
+                else:
+                    blk = blk - dt * (1 - th) * self.S[i, j] * M
+                Be[:, pi:pi + n1, pj:pj + n1] = blk
+        return Be
+
+    def element_matrix_prec(self, cells, **kw):
+        """``prec = pu + pp + ppt`` (mpettotalpressuresolver.py:276-283)."""
+        d, J = self.d, self.A
+        sp_ = self.space
+        n2, n1, nloc = sp_.n2, sp_.n1, sp_.nloc
+        mu, lmbda = convert_to_mu_lmbda(self.E, self.nu)
+        dt, th = self.dt, self.theta
+        G, D, M, Lp = self.element_blocks(cells)
+        Pe = np.zeros((len(cells), nloc, nloc))
+        trG = np.einsum("cabmm->cab", G)
+        for k in range(d):
+            Pe[:, k * n2:(k + 1) * n2, k * n2:(k + 1) * n2] = mu * trG
+        p0 = d * n2
+        Pe[:, p0:p0 + n1, p0:p0 + n1] = M
+        for i in range(J):
+            pi = d * n2 + (i + 1) * n1
+            offsum = sum(self.S[i, j] for j in range(J) if j != i)
+            mass = self.alpha[i] ** 2 / lmbda + self.c[i] + dt * th * offsum
+            Pe[:, pi:pi + n1, pi:pi + n1] = mass * M + dt * th * self.K[i] * Lp
+        return Pe

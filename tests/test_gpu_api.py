@@ -11,9 +11,9 @@ from oracle.mpet import MPETOracle, Coef
 PI = np.pi
 
 
-def _mms_problem(n, J, theta, dt, T, nonsym=False):
-    from waterscapes_b200.mpet import (MPETProblem, MPETSolver, UnitCubeMesh, Constant, Expression,
-                                       CompiledSubDomain, FacetNormal)
+def _mms_problem(n, J, theta, dt, T, nonsym=False, total_pressure=False):
+    from waterscapes_b200.mpet import (MPETProblem, MPETSolver, MPETTotalPressureSolver, UnitCubeMesh, Constant,
+                                       Expression, CompiledSubDomain, FacetNormal)
     S = ((0.0, 2.0), (1.0, 0.0)) if nonsym else ((0.0, 1.0), (1.0, 0.0))
     params = dict(J=J, E=2.2, nu=0.4545, alpha=(0.5, 0.5), c=(1.0, 1.0), K=(1.0, 1.0), S=S)
     mesh = UnitCubeMesh(n)
@@ -41,13 +41,15 @@ def _mms_problem(n, J, theta, dt, T, nonsym=False):
         on_boundary.mark(problem.continuity_boundary_markers[i], 0)
     right.mark(problem.continuity_boundary_markers[0], 1)
     top.mark(problem.continuity_boundary_markers[1], 2)
-    solver = MPETSolver(problem, dict(dt=dt, theta=theta, T=T))
+    cls = MPETTotalPressureSolver if total_pressure else MPETSolver
+    solver = cls(problem, dict(dt=dt, theta=theta, T=T))
     return mesh, params, problem, solver
 
 
-def _oracle_twin(n, params, theta, dt, T):
+def _oracle_twin(n, params, theta, dt, T, total_pressure=False):
+    from oracle.mpet import MPETTotalPressureOracle
     mesh = unit_cube_mesh(n)
-    o = MPETOracle(mesh, params, dt=dt, theta=theta, T=T)
+    o = (MPETTotalPressureOracle if total_pressure else MPETOracle)(mesh, params, dt=dt, theta=theta, T=T)
     J = params["J"]
     o.u_bar = Coef(fn=lambda x, t: 0.1 * np.stack([np.cos(PI * x[:, 0]) * np.sin(PI * x[:, 1]) * np.sin(PI * x[:, 2]),
                                                    np.sin(PI * x[:, 0]) * np.cos(PI * x[:, 1]) * np.sin(PI * x[:, 2]),

@@ -1,0 +1,101 @@
+"""GPU parity of the total-pressure formulation (mpettotalpressuresolver.py:164-512)
+against the oracle's twin: assembled A / P / b through the C-ABI, the reference-facing
+MPETTotalPressureSolver time loop (direct preset and MINRES + block AMG), and nu-robustness of the
+iteration count, which is why the reference carries this formulation."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle.mesh import unit_cube_mesh
+from oracle.mpet import MPETTotalPressureOracle
+from tests.test_gpu_assembly import PARAMS
+from tests.test_gpu_api import _mms_problem, _oracle_twin, _init, _rel
+
+
+@pytest.mark.parametrize("n,J,theta,jitter", [(3, 2, 1.0, 0.0), (4, 1, 0.5, 0.2), (3, 4, 0.5, 0.2)])
+def test_total_pressure_assembly(n, J, theta, jitter):
+    from waterscapes_b200.engine import Engine
+    mesh = unit_cube_mesh(n, jitter=jitter)
+    params = PARAMS[J]
+    dt = 0.05
+    o = MPETTotalPressureOracle(mesh, params, dt=dt, theta=theta)
+    eng = Engine(0)
+    eng.set_mesh(mesh.coords, mesh.cells.astype(np.int32), J + 1)          # field 0 = total pressure
+    eng.set_params_total_pressure(params["E"], params["nu"], params["alpha"], params["K"], params["S"],
+                                  params["c"], dt, theta)
+    assert eng.sizes["N"] == o.space.N
+    assert np.array_equal(eng.cell_dofs().cpu().numpy(), o.space.cell_dofs)
+    rowptr, cols = eng.pattern()
+    ip, ix = o.pattern()
+    assert np.array_equal(rowptr.cpu().numpy(), ip) and np.array_equal(cols.cpu().numpy(), ix)
+    eng.assemble_lhs()
+    Ao = o.on_pattern(o.assemble_lhs())
+    assert _rel(eng.values(0).cpu().numpy(), Ao.data) < 1e-12
+    eng.assemble_prec()
+    Po = o.on_pattern(o.assemble_prec())
+    assert _rel(eng.values(3).cpu().numpy(), Po.data) < 1e-12
+    # previous-state load and SpMV
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(o.space.N)
+    o.up_ = x.copy()
+    xd = torch.as_tensor(x, device="cuda")
+    bd = torch.empty_like(xd)
+    eng.rhs_prev(xd, bd)
+    bo = o.assemble_L()
+    assert _rel(bd.cpu().numpy(), bo) < 1e-12
+    eng.spmv(xd, bd)
+    assert _rel(bd.cpu().numpy(), Ao @ x) < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_total_pressure_solver_matches_oracle_time_loop(theta):
+    n, J, dt, T = 4, 2, 0.1, 0.3
+    mesh, params, problem, solver = _mms_problem(n, J, theta, dt, T, total_pressure=True)
+    o = _oracle_twin(n, params, theta, dt, T, total_pressure=True)
+    _init(solver, o)
+    A = solver._assemble_system().to_scipy()
+    Ao = o.on_pattern(o.assemble_lhs())
+    assert _rel(A.data, Ao.data) < 1e-12
+    bo, dofs, vals = o.rhs(0.0)
+    bcs = solver.bcs[0] + solver.bcs[1]
+    solver._sync_dirichlet(bcs)
+    b, _ = solver._rhs(problem.time, 0.0, dt, theta, bcs)
+    assert _rel(b.get_local(), bo) < 1e-12
+    problem.time.assign(0.0)
+    ref = list((up.copy(), t) for up, t in o.solve_direct())
+    k = 0
+    for up, t in solver.solve():
+        xo, to = ref[k]
+        assert abs(t - to) < 1e-12
+        x = up.vector().get_local()
+        sp_ = o.space
+        nu = 3 * sp_.N2
+        errs = [_rel(x[:nu], xo[:nu])] + [_rel(x[sp_.p_dofs(i)], xo[sp_.p_dofs(i)]) for i in range(J + 1)]
+        assert max(errs) < 1e-8, (t, errs)
+        k += 1
+    assert k == len(ref) == 3
+    u, p0, p1, p2 = solver.up.split(deepcopy=True)
+    assert u.values.shape == (o.space.N2, 3) and p0.values.shape == (o.space.Nv,)
+
+
+def test_total_pressure_iterative_is_nu_robust():
+    """MINRES + block-diagonal AMG on the brain parameters (nu = 0.4999): the total-pressure system
+    needs a small fraction of the iterations of the standard two-field system."""
+    from waterscapes_b200.workloads import make_problem
+    from waterscapes_b200.mpet import MPETSolver, MPETTotalPressureSolver
+    counts = {}
+    for cls in (MPETSolver, MPETTotalPressureSolver):
+        problem, sp, init = make_problem("cfg5", 8)
+        solver = cls(problem, dict(sp, direct_solver=False, krylov_rtol=1e-6, T=sp["dt"]))
+        J = int(problem.params["J"])
+        for i in range(J):                               # initial pressures = boundary data
+            solver.up_.set_sub(solver._net_sub(i), problem.p_bar[i])
+        for up, t in solver.solve():
+            pass
+        assert solver.solver_monitor["last"]["converged"]
+        counts[cls.__name__] = solver.solver_monitor["niter"][-1]
+    print(counts)
+    assert counts["MPETTotalPressureSolver"] * 3 < counts["MPETSolver"], counts

@@ -125,7 +125,7 @@ def _exact_solutions(params):
         fs = [[fn(e) for e in row] for row in exprs]
         return lambda X, tt: np.stack([np.stack([f_(X, tt) for f_ in row], axis=1) for row in fs], axis=1)
 
-    return dict(u=vec(u), grad_u=ten(grad_u), p=[fn(pi_) for pi_ in p[1:]],
+    return dict(u=vec(u), grad_u=ten(grad_u), p=[fn(pi_) for pi_ in p[1:]], p_total=fn(p[0]),
                 grad_p=[vec(gp) for gp in grad_p[1:]], f=vec(f), g=[fn(gi) for gi in g],
                 sigma=ten(sigma))
 
@@ -196,5 +196,67 @@ def test_convergence_mpetsolver(theta, ns, ms):
     assert u_L2[-1] > 1.70
     assert p0_L2[-1] > 1.70
     assert p1_L2[-1] > 1.70
+    assert p0_H1[-1] > 0.95
+    assert p1_H1[-1] > 0.95
+
+
+# ------------------------------------------------------------------------- total-pressure MMS
+def _single_run_total_pressure(n, M, theta):
+    """test_convergence_totalpressuresolver.py:103-182."""
+    from oracle.mpet import MPETTotalPressureOracle
+    T = 1.0
+    dt = float(T / M)
+    params = dict(J=2, c=(1.0, 1.0), alpha=(1.0, 1.0), K=(1.0, 1.0), S=((1.0, 1.0), (1.0, 1.0)), E=1.0, nu=0.35)
+    ex = _exact_solutions(params)
+    mesh = unit_square_mesh(n)
+    o = MPETTotalPressureOracle(mesh, params, dt=dt, theta=theta, T=T)
+    o.f = Coef(fn=ex["f"], degree=3)
+    o.g = [Coef(fn=ex["g"][i], degree=3) for i in range(2)]
+    o.u_bar = Coef(fn=ex["u"], degree=3)
+    o.s = Coef(fn=ex["sigma"], degree=4)       # sigma_ex * normal, sigma = 2 mu eps(u) + p0 I
+    o.s_times_normal = True
+    o.p_bar = [Coef(fn=ex["p"][i], degree=3) for i in range(2)]
+    F = o.facets
+    o.momentum_markers[:] = 0
+    xm = mesh.coords[F["vertices"]]
+    right = np.all(np.abs(xm[:, :, 0] - 1.0) < 3e-16, axis=1)     # near(x[0], 1.0)
+    o.momentum_markers[right] = 1
+    for i in range(2):
+        o.continuity_markers[i][:] = 0
+    # initial conditions, total pressure included (test_convergence_totalpressuresolver.py:156-163)
+    sp_ = o.space
+    x2 = sp_.node2_coords()
+    u0 = ex["u"](x2, 0.0)
+    for k in range(2):
+        o.up_[sp_.u_dofs(k)] = u0[:, k]
+    o.up_[sp_.p_dofs(0)] = ex["p_total"](mesh.coords, 0.0)
+    for i in range(2):
+        o.up_[sp_.p_dofs(i + 1)] = ex["p"][i](mesh.coords, 0.0)
+    for up, t in o.solve_direct():
+        pass
+    # errors of (u, p1, p2): drop the total pressure from the split
+    err = o.error_norms(up, ex["u"], ex["p"], t, qdeg=7, grad_u=ex["grad_u"], grad_p=ex["grad_p"],
+                        fields=[1, 2])
+    h = 2 * min(_circumradius(mesh))
+    return err["u_L2"], err["u_H1"], err["p_L2"], err["p_H1"], h
+
+
+@pytest.mark.parametrize("theta,ns,ms", [(0.5, [8, 16, 32], [4, 8, 16]),
+                                         (1.0, [8, 16, 32], [8, 32, 128])])
+def test_convergence_totalpressuresolver(theta, ns, ms):
+    """test_convergence_totalpressuresolver.py:184-253 (thresholds :237-242)."""
+    res = [_single_run_total_pressure(n, m, theta) for n, m in zip(ns, ms)]
+    hs = [r[4] for r in res]
+    u_L2 = _rates([r[0] for r in res], hs)
+    u_H1 = _rates([r[1] for r in res], hs)
+    p0_L2 = _rates([r[2][0] for r in res], hs)
+    p1_L2 = _rates([r[2][1] for r in res], hs)
+    p0_H1 = _rates([r[3][0] for r in res], hs)
+    p1_H1 = _rates([r[3][1] for r in res], hs)
+    print(u_L2, u_H1, p0_L2, p1_L2, p0_H1, p1_H1)
+    assert u_L2[-1] > 1.70
+    assert u_H1[-1] > 1.70
+    assert p0_L2[-1] > 1.85
+    assert p1_L2[-1] > 1.87
     assert p0_H1[-1] > 0.95
     assert p1_H1[-1] > 0.95

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <cstdlib>
 
 namespace {
 
@@ -892,11 +893,11 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         AmgHierarchy* H = new AmgHierarchy();
         H->nrhs = 4;   // W = 4: three components + pad
         AmgLevel L0;
-        L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->mu, ctx->bc_mask, &L0.dinv, st);
+        L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->coef.p_mu, ctx->bc_mask, &L0.dinv, st);
         if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P2W4;
         H->levels.push_back(L0);
         AmgLevel L1;
-        L1.A = masked_block(ctx, ctx->g11, ctx->l11, ctx->mu, ctx->bc_mask /* vertices are the first Nv nodes */,
+        L1.A = masked_block(ctx, ctx->g11, ctx->l11, ctx->coef.p_mu, ctx->bc_mask /* vertices are the first Nv nodes */,
                             &L1.dinv, st);
         if (dist_active(ctx)) L1.halo_plan = DIST_PLAN_P1W4;
         HostCsr P = p2_to_p1(nv, ctx->Ne, edge_v, mask2);
@@ -923,9 +924,36 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-// r, z in the solver-internal layout (layout.cuh)
+// r, z in the solver-internal layout (layout.cuh).  The block-diagonal preconditioner is A + 1 independent
+// V-cycles; on one GPU the per-network cycles (dozens of small launches each) run on their own high-priority
+// streams beside the displacement cycle and join before returning.  Multi-GPU keeps one stream: the halo
+// exchanges of all cycles share one NCCL communicator and must be issued in one order on every rank.
 void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
+    static const bool want_streams = []() { const char* e = getenv("MPET_PC_STREAMS"); return !(e && e[0] == '0'); }();
+    const bool fork = want_streams && ctx->A > 0 && !dist_active(ctx);
+    if (fork) {
+        if (ctx->pc_streams_ready < ctx->A) {
+            int lo = 0, hi = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi = numerically lowest = highest priority
+            if (!ctx->pc_fork) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->pc_fork, cudaEventDisableTiming));
+            for (int i = ctx->pc_streams_ready; i < ctx->A; ++i) {
+                CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->pc_stream[i], cudaStreamNonBlocking, hi));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ctx->pc_join[i], cudaEventDisableTiming));
+            }
+            ctx->pc_streams_ready = ctx->A;
+        }
+        CUDA_CHECK(cudaEventRecord(ctx->pc_fork, st));
+        for (int i = 0; i < ctx->A; ++i) {
+            const int64_t off = 4 * n2 + (int64_t)i * nv;
+            CUDA_CHECK(cudaStreamWaitEvent(ctx->pc_stream[i], ctx->pc_fork, 0));
+            vcycle<1>(ctx, *ctx->amg_p[i], 0, r + off, z + off, done, ctx->pc_stream[i]);
+            CUDA_CHECK(cudaEventRecord(ctx->pc_join[i], ctx->pc_stream[i]));
+        }
+        vcycle<4>(ctx, *ctx->amg_u, 0, r, z, done, st);
+        for (int i = 0; i < ctx->A; ++i) CUDA_CHECK(cudaStreamWaitEvent(st, ctx->pc_join[i], 0));
+        return;
+    }
     vcycle<4>(ctx, *ctx->amg_u, 0, r, z, done, st);
     for (int i = 0; i < ctx->A; ++i) {
         int64_t off = 4 * n2 + (int64_t)i * nv;

@@ -122,6 +122,8 @@ void mpet_destroy(mpet_ctx* ctx) {
         krylov_free(ctx);
         amg_free(ctx);
         dist_free(ctx);
+        for (int i = 0; i < ctx->pc_streams_ready; ++i) { cudaStreamDestroy(ctx->pc_stream[i]); cudaEventDestroy(ctx->pc_join[i]); }
+        if (ctx->pc_fork) cudaEventDestroy(ctx->pc_fork);
         for (void* p : ctx->allocs) cudaFree(p);
     } catch (...) {
     }
@@ -184,23 +186,91 @@ int mpet_get_pattern(mpet_ctx* ctx, int64_t* rowptr, int32_t* cols, void* stream
     MPET_CATCH(ctx)
 }
 
+static void store_material(mpet_ctx* ctx, int J, double E, double nu, const double* alpha, const double* K,
+                           const double* S, const double* c, double dt, double theta) {
+    ctx->E = E;
+    ctx->nu = nu;
+    ctx->mu = E / (2.0 * (1.0 + nu));                           // mpetproblem.py:13-16
+    ctx->lmbda = nu * E / ((1.0 - 2.0 * nu) * (1.0 + nu));
+    for (int i = 0; i < J; ++i) {
+        ctx->alpha[i] = alpha[i];
+        ctx->K[i] = K[i];
+        ctx->c[i] = c[i];
+        for (int j = 0; j < J; ++j) ctx->S[i * J + j] = S[i * J + j];
+    }
+    ctx->dt = dt;
+    ctx->theta = theta;
+    ctx->coef = BlockCoefs();
+}
+
 int mpet_set_params(mpet_ctx* ctx, double E, double nu, const double* alpha, const double* K,
                     const double* S, const double* c, double dt, double theta) {
     MPET_TRY(ctx)
     const int A = ctx->A;
     MPET_REQUIRE(ctx->Nc > 0, "mpet_set_mesh must be called first");
-    ctx->E = E;
-    ctx->nu = nu;
-    ctx->mu = E / (2.0 * (1.0 + nu));                           // mpetproblem.py:13-16
-    ctx->lmbda = nu * E / ((1.0 - 2.0 * nu) * (1.0 + nu));
+    store_material(ctx, A, E, nu, alpha, K, S, c, dt, theta);
+    // standard formulation, a = lhs(F) / L = rhs(F) of mpetsolver.py:196-201,260-261; prec :268-272
+    BlockCoefs& C = ctx->coef;
+    const double dth = dt * theta, d1 = dt * (1.0 - theta);
+    C.uu_mu = ctx->mu;
+    C.uu_lam = ctx->lmbda;
+    C.p_mu = ctx->mu;
     for (int i = 0; i < A; ++i) {
-        ctx->alpha[i] = alpha[i];
-        ctx->K[i] = K[i];
-        ctx->c[i] = c[i];
-        for (int j = 0; j < A; ++j) ctx->S[i * A + j] = S[i * A + j];
+        double offsum = 0;
+        for (int j = 0; j < A; ++j)
+            if (j != i) offsum += S[i * A + j];
+        C.cup[i] = C.cpu[i] = -alpha[i];
+        C.cl[i] = -dth * K[i];
+        C.rl[i] = d1 * K[i];
+        C.ru[i] = 1.0;                       // -alpha_i int psi div(u^-) is A's own (p_i ; u) block applied to u^-
+        C.pm[i] = c[i] + dth * offsum;
+        C.pk[i] = dth * K[i];
+        for (int j = 0; j < A; ++j) {
+            C.cm[i * A + j] = (i == j) ? (-c[i] - dth * offsum) : dth * S[i * A + j];
+            C.rm[i * A + j] = (i == j) ? (-c[i] + d1 * offsum) : -d1 * S[i * A + j];
+        }
     }
-    ctx->dt = dt;
-    ctx->theta = theta;
+    ctx->formulation = 0;
+    ctx->params_set = true;
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_params_total_pressure(mpet_ctx* ctx, double E, double nu, const double* alpha, const double* K,
+                                   const double* S, const double* c, double dt, double theta) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->Nc > 0, "mpet_set_mesh must be called first");
+    MPET_REQUIRE(ctx->A >= 1, "the total-pressure formulation needs n_networks + 1 P1 fields (mpet_set_mesh)");
+    const int NP = ctx->A, J = NP - 1;       // field 0 = total pressure p0, field i+1 = network i
+    store_material(ctx, J, E, nu, alpha, K, S, c, dt, theta);
+    // F of mpettotalpressuresolver.py:267-274 split with lhs/rhs; prec :276-283
+    BlockCoefs& C = ctx->coef;
+    const double dth = dt * theta, d1 = dt * (1.0 - theta), il = 1.0 / ctx->lmbda;
+    C.uu_mu = ctx->mu;                        // 2 mu eps(u):eps(v) = mu (grad u:grad v + grad u^T:grad v)
+    C.uu_lam = 0.0;
+    C.p_mu = ctx->mu;
+    C.cup[0] = C.cpu[0] = 1.0;                // + p0 div v ;  + div u w0
+    C.cm[0] = -il;                            // -1/lambda p0 w0
+    C.pm[0] = 1.0;                            // ppt = p0 w0
+    for (int i = 0; i < J; ++i) {
+        const int r = i + 1;
+        double offsum = 0;
+        for (int j = 0; j < J; ++j)
+            if (j != i) offsum += S[i * J + j];
+        C.cm[0 * NP + r] = -alpha[i] * il;    // -alpha_i/lambda p_i w0
+        C.cm[r * NP + 0] = -alpha[i] * il;    // -alpha_i/lambda p0 w_i
+        C.rm[r * NP + 0] = -alpha[i] * il;    // -alpha_i/lambda p0^- w_i   (rhs sign: see DESIGN.md)
+        C.cl[r] = -dth * K[i];
+        C.rl[r] = d1 * K[i];
+        C.pm[r] = alpha[i] * alpha[i] * il + c[i] + dth * offsum;
+        C.pk[r] = dth * K[i];
+        for (int j = 0; j < J; ++j) {
+            const int q = j + 1;
+            const double aa = alpha[i] * alpha[j] * il;
+            C.cm[r * NP + q] = -aa + ((i == j) ? (-c[i] - dth * offsum) : dth * S[i * J + j]);
+            C.rm[r * NP + q] = -aa + ((i == j) ? (-c[i] + d1 * offsum) : -d1 * S[i * J + j]);
+        }
+    }
+    ctx->formulation = 1;
     ctx->params_set = true;
     MPET_CATCH(ctx)
 }

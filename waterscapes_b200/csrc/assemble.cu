@@ -208,7 +208,7 @@ k_asm21(const int32_t* __restrict__ rp21, const int32_t* __restrict__ col21,
         const double* __restrict__ geom, const int32_t* __restrict__ rp22,
         const int32_t* __restrict__ rp12, const int32_t* __restrict__ t21to12,
         const int64_t* __restrict__ rowptr, int64_t n2, int64_t nv, int64_t nnz21, int A,
-        const double* __restrict__ alpha, double* __restrict__ vals) {
+        const double* __restrict__ cup, const double* __restrict__ cpu, double* __restrict__ vals) {
     __shared__ double sQ[120];
     for (int i = threadIdx.x; i < 120; i += blockDim.x) sQ[i] = c_Q21[i];
     __syncthreads();
@@ -234,25 +234,24 @@ k_asm21(const int32_t* __restrict__ rp21, const int32_t* __restrict__ col21,
     int32_t d12 = rp12[v + 1] - rp12[v];
     int32_t jt = t21to12[e] - rp12[v];
     for (int i = 0; i < A; ++i) {
-        double al = -alpha[i];
+        const double au = cup[i], ap = cpu[i];
         int64_t prow = rowptr[3 * n2 + i * nv + v];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            vals[rowptr[k * n2 + a] + 3 * (int64_t)d22 + (int64_t)i * d21 + j] = al * D[k];
-            vals[prow + (int64_t)k * d12 + jt] = al * D[k];
+            vals[rowptr[k * n2 + a] + 3 * (int64_t)d22 + (int64_t)i * d21 + j] = au * D[k];
+            vals[prow + (int64_t)k * d12 + jt] = ap * D[k];
         }
     }
 }
 
 // One thread per P1xP1 entry: mass and stiffness; writes the A^2 pressure-block values
-//   (i,i): -c_i M - dt theta K_i L - dt theta (sum_{j!=i} S_ij) M ;  (i,j): + dt theta S_ij M
+//   (i,j): cm[i][j] M + delta_ij cl[i] L      (BlockCoefs, ctx.h)
 __global__ void __launch_bounds__(256)
 k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
         const uint32_t* __restrict__ glist, const double* __restrict__ geom,
         const int32_t* __restrict__ rp12, const int64_t* __restrict__ rowptr, int64_t n2, int64_t nv,
-        int64_t nnz11, int A, const double* __restrict__ cdiag, const double* __restrict__ kdiag,
-        const double* __restrict__ soff, double* __restrict__ vals, double* __restrict__ m11,
-        double* __restrict__ l11) {
+        int64_t nnz11, int A, const double* __restrict__ cm, const double* __restrict__ cl,
+        double* __restrict__ vals, double* __restrict__ m11, double* __restrict__ l11) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz11) return;
     int64_t v = row_of_entry(rp11, nv, (int32_t)e);
@@ -284,7 +283,8 @@ k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
     for (int i = 0; i < A; ++i) {
         int64_t base = rowptr[3 * n2 + i * nv + v] + 3 * (int64_t)d12 + jj;
         for (int j = 0; j < A; ++j) {
-            double val = (i == j) ? (cdiag[i] * M + kdiag[i] * L) : soff[i * A + j] * M;
+            double val = cm[i * A + j] * M;
+            if (i == j) val += cl[i] * L;
             vals[base + (int64_t)j * d11] = val;
         }
     }
@@ -345,41 +345,32 @@ void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
     MPET_REQUIRE(ctx->params_set, "mpet_set_params must be called before assembly");
     const int A = ctx->A;
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
-    const double dth = ctx->dt * ctx->theta;
-    double cdiag[MPET_MAX_NETWORKS], kdiag[MPET_MAX_NETWORKS], soff[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
-    for (int i = 0; i < A; ++i) {
-        double offsum = 0;
-        for (int j = 0; j < A; ++j)
-            if (j != i) offsum += ctx->S[i * A + j];
-        cdiag[i] = -ctx->c[i] - dth * offsum;
-        kdiag[i] = -dth * ctx->K[i];
-        for (int j = 0; j < A; ++j) soff[i * A + j] = dth * ctx->S[i * A + j];
-    }
+    const BlockCoefs& C = ctx->coef;
     std::vector<void*> tmp;
-    double* d_alpha = upload_small(ctx, ctx->alpha, A, st, tmp);
-    double* d_cdiag = upload_small(ctx, cdiag, A, st, tmp);
-    double* d_kdiag = upload_small(ctx, kdiag, A, st, tmp);
-    double* d_soff = upload_small(ctx, soff, A * A, st, tmp);
+    double* d_cup = upload_small(ctx, C.cup, A, st, tmp);
+    double* d_cpu = upload_small(ctx, C.cpu, A, st, tmp);
+    double* d_cm = upload_small(ctx, C.cm, A * A, st, tmp);
+    double* d_cl = upload_small(ctx, C.cl, A, st, tmp);
 
     const int threads = 256;
     if (ctx->k22) {
         k_asm22<true, true, false><<<grid_for(n2 * 32, threads), threads, 0, st>>>(
-            ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, n2, ctx->mu, ctx->lmbda,
+            ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, n2, C.uu_mu, C.uu_lam,
             ctx->vals, ctx->k22, nullptr);
     } else {
         k_asm22<true, false, false><<<grid_for(n2 * 32, threads), threads, 0, st>>>(
-            ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, n2, ctx->mu, ctx->lmbda,
+            ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, n2, C.uu_mu, C.uu_lam,
             ctx->vals, nullptr, nullptr);
     }
     LAUNCH_CHECK(ctx);
     if (A > 0) {
         k_asm21<<<grid_for(ctx->g21.nnz, threads), threads, 0, st>>>(
             ctx->g21.rowptr, ctx->g21.col, ctx->g21.gptr, ctx->g21.glist, ctx->geom, ctx->g22.rowptr,
-            ctx->g12.rowptr, ctx->t21to12, ctx->rowptr, n2, nv, ctx->g21.nnz, A, d_alpha, ctx->vals);
+            ctx->g12.rowptr, ctx->t21to12, ctx->rowptr, n2, nv, ctx->g21.nnz, A, d_cup, d_cpu, ctx->vals);
         LAUNCH_CHECK(ctx);
         k_asm11<<<grid_for(ctx->g11.nnz, threads), threads, 0, st>>>(
             ctx->g11.rowptr, ctx->g11.gptr, ctx->g11.glist, ctx->geom, ctx->g12.rowptr, ctx->rowptr, n2, nv,
-            ctx->g11.nnz, A, d_cdiag, d_kdiag, d_soff, ctx->vals, ctx->m11, ctx->l11);
+            ctx->g11.nnz, A, d_cm, d_cl, ctx->vals, ctx->m11, ctx->l11);
         LAUNCH_CHECK(ctx);
     }
     CUDA_CHECK(cudaStreamSynchronize(st));   // small coefficient uploads are freed below
@@ -410,19 +401,12 @@ void assemble_prec(mpet_ctx* ctx, cudaStream_t st) {
     if (!ctx->lhs_ready) {   // m11 / l11 not yet computed
         k_asm11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(
             ctx->g11.rowptr, ctx->g11.gptr, ctx->g11.glist, ctx->geom, ctx->g12.rowptr, ctx->rowptr, ctx->N2,
-            ctx->Nv, ctx->g11.nnz, A, nullptr, nullptr, nullptr, nullptr, ctx->m11, ctx->l11);
+            ctx->Nv, ctx->g11.nnz, A, nullptr, nullptr, nullptr, ctx->m11, ctx->l11);
         LAUNCH_CHECK(ctx);
     }
     if (!ctx->pp11) ctx->pp11 = dev_alloc<double>(ctx, (int64_t)A * ctx->g11.nnz);
-    const double dth = ctx->dt * ctx->theta;
-    double cm[MPET_MAX_NETWORKS], ck[MPET_MAX_NETWORKS];
-    for (int i = 0; i < A; ++i) {
-        double offsum = 0;
-        for (int j = 0; j < A; ++j)
-            if (j != i) offsum += ctx->S[i * A + j];
-        cm[i] = ctx->c[i] + dth * offsum;     // mpetsolver.py:270-271
-        ck[i] = dth * ctx->K[i];
-    }
+    const double* cm = ctx->coef.pm;      // mpetsolver.py:270-271 / mpettotalpressuresolver.py:279-282
+    const double* ck = ctx->coef.pk;
     std::vector<void*> tmp;
     double* d_cm = upload_small(ctx, cm, A, st, tmp);
     double* d_ck = upload_small(ctx, ck, A, st, tmp);

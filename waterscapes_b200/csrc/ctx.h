@@ -90,6 +90,21 @@ struct Prof {
     int64_t cnt[PROF_NCAT] = {0};
 };
 
+// Coefficient tables of the generic Taylor-Hood block system [P2]^3 x [P1]^NP that the kernels assemble.
+// Both formulations of the reference reduce to it (filled by mpet_set_params / mpet_set_params_total_pressure):
+//   (u_k,a ; u_l,b)  = uu_mu * (delta_kl int grad phi_a . grad phi_b + int d_l phi_a d_k phi_b) + uu_lam * int d_k phi_a d_l phi_b
+//   (u_k,a ; p_i,m)  = cup[i] * int psi_m d_k phi_a          (p_i,m ; u_l,b) = cpu[i] * int psi_m d_l phi_b
+//   (p_i,m ; p_j,n)  = cm[i][j] * M_mn + delta_ij * cl[i] * L_mn          (M: P1 mass, L: P1 stiffness)
+//   previous-state load of row p_i:  sum_j rm[i][j] M p_j^- + rl[i] L p_i^- + ru[i] * (the assembled (p_i ; u) block) u^-
+//   preconditioner: p_mu * int grad phi_a . grad phi_b per displacement component; pm[i] M + pk[i] L per P1 field
+struct BlockCoefs {
+    double uu_mu = 0, uu_lam = 0, p_mu = 0;
+    double cup[MPET_MAX_NETWORKS] = {}, cpu[MPET_MAX_NETWORKS] = {};
+    double cm[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS] = {}, cl[MPET_MAX_NETWORKS] = {};
+    double rm[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS] = {}, rl[MPET_MAX_NETWORKS] = {}, ru[MPET_MAX_NETWORKS] = {};
+    double pm[MPET_MAX_NETWORKS] = {}, pk[MPET_MAX_NETWORKS] = {};
+};
+
 struct mpet_ctx {
     int device = 0;
     Prof prof;
@@ -127,6 +142,8 @@ struct mpet_ctx {
     double E = 0, nu = 0, mu = 0, lmbda = 0, dt = 0, theta = 1;
     double alpha[MPET_MAX_NETWORKS], K[MPET_MAX_NETWORKS], c[MPET_MAX_NETWORKS];
     double S[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
+    BlockCoefs coef;             // what the kernels read (either formulation)
+    int formulation = 0;         // 0: standard (mpetsolver.py), 1: total pressure (mpettotalpressuresolver.py)
     bool params_set = false, lhs_ready = false, prec_ready = false;
 
     // Dirichlet
@@ -148,6 +165,10 @@ struct mpet_ctx {
     AmgHierarchy* amg_u = nullptr;              // scalar P2 block, 3 right-hand sides
     AmgHierarchy* amg_p[MPET_MAX_NETWORKS] = {};  // one per network
     double* jac_dinv = nullptr;                 // Jacobi preconditioner (pc = 1)
+    // the per-network V-cycles are independent of the displacement V-cycle: they run on their own streams
+    cudaStream_t pc_stream[MPET_MAX_NETWORKS] = {};
+    cudaEvent_t pc_fork = nullptr, pc_join[MPET_MAX_NETWORKS] = {};
+    int pc_streams_ready = 0;
 };
 
 // ---- helpers --------------------------------------------------------------------------------

@@ -2,9 +2,10 @@
 //
 //  * k_rhs_prev     : b = assemble(L), L = rhs(F)  (mpetsolver.py:198-201,261,356,433,528) evaluated
 //                     as a sparse operator acting on the previous state instead of a cell loop:
-//                     pressure row (i,v) = [A's own "pu" coupling block] * u_prev
-//                                        + [(-c_i + dt(1-theta) sum_j S_ij) M + dt(1-theta) K_i L] p_i_prev
-//                                        - dt(1-theta) sum_{j != i} S_ij M p_j_prev ;  momentum rows = 0.
+//                     pressure row (i,v) = ru[i] * [A's own "pu" coupling block] * u_prev
+//                                        + sum_j rm[i][j] M p_j_prev + rl[i] L p_i_prev ;  momentum rows = 0
+//                     (BlockCoefs in ctx.h; standard formulation: ru = 1, rm[i][i] = -c_i + dt(1-theta) sum_j S_ij,
+//                     rl[i] = dt(1-theta) K_i, rm[i][j] = -dt(1-theta) S_ij).
 //  * k_bc_values    : export-time application of bc.apply(A) / apply_symmetric(bc, A)
 //                     (mpetsolver.py:343-344,418-419; bc_symmetric.py:11-22).  The solver itself never
 //                     modifies A: it masks rows on the fly (spmv.cu).
@@ -19,7 +20,7 @@ k_rhs_prev(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
            const double* __restrict__ vals, const int32_t* __restrict__ rp12,
            const int32_t* __restrict__ rp11, const int32_t* __restrict__ col11,
            const double* __restrict__ m11, const double* __restrict__ l11, int64_t n2, int64_t nv, int A,
-           const double* __restrict__ coef /* [A] cprev, [A] kprev, [A*A] sprev */,
+           const double* __restrict__ coef /* [A] ru, [A] rl, [A*A] rm */,
            const double* __restrict__ up, double* __restrict__ b) {
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -30,14 +31,17 @@ k_rhs_prev(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
     int64_t s = rowptr[row];
     int32_t d12 = rp12[v + 1] - rp12[v];
     double sum = 0.0;
-    for (int32_t t = lane; t < 3 * d12; t += 32) sum += vals[s + t] * up[cols[s + t]];
+    const double ru = coef[i];
+    if (ru != 0.0) {
+        for (int32_t t = lane; t < 3 * d12; t += 32) sum += vals[s + t] * up[cols[s + t]];
+        sum *= ru;
+    }
     const double* pbase = up + 3 * n2;
     for (int32_t e = rp11[v] + lane; e < rp11[v + 1]; e += 32) {
         int32_t vp = col11[e];
         double M = m11[e], L = l11[e];
-        double acc = (coef[i] * M + coef[A + i] * L) * pbase[(int64_t)i * nv + vp];
-        for (int j = 0; j < A; ++j)
-            if (j != i) acc += coef[2 * A + i * A + j] * M * pbase[(int64_t)j * nv + vp];
+        double acc = coef[A + i] * L * pbase[(int64_t)i * nv + vp];
+        for (int j = 0; j < A; ++j) acc += coef[2 * A + i * A + j] * M * pbase[(int64_t)j * nv + vp];
         sum += acc;
     }
 #pragma unroll
@@ -130,15 +134,11 @@ void rhs_prev(mpet_ctx* ctx, const double* up, double* b, cudaStream_t st) {
     const int A = ctx->A;
     CUDA_CHECK(cudaMemsetAsync(b, 0, sizeof(double) * 3 * ctx->N2, st));
     if (A == 0) return;
-    const double d1 = ctx->dt * (1.0 - ctx->theta);
     double coef[2 * MPET_MAX_NETWORKS + MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
     for (int i = 0; i < A; ++i) {
-        double offsum = 0;
-        for (int j = 0; j < A; ++j)
-            if (j != i) offsum += ctx->S[i * A + j];
-        coef[i] = -ctx->c[i] + d1 * offsum;
-        coef[A + i] = d1 * ctx->K[i];
-        for (int j = 0; j < A; ++j) coef[2 * A + i * A + j] = -d1 * ctx->S[i * A + j];
+        coef[i] = ctx->coef.ru[i];
+        coef[A + i] = ctx->coef.rl[i];
+        for (int j = 0; j < A; ++j) coef[2 * A + i * A + j] = ctx->coef.rm[i * A + j];
     }
     double* d_coef = nullptr;
     int n = 2 * A + A * A;
@@ -157,7 +157,7 @@ void export_values(mpet_ctx* ctx, int which, double* out, cudaStream_t st) {
         MPET_REQUIRE(ctx->prec_ready, "mpet_assemble_prec must run first");
         k_expand_prec<<<grid_for(ctx->N * 32, 256), 256, 0, st>>>(
             ctx->rowptr, ctx->g22.rowptr, ctx->g21.rowptr, ctx->g12.rowptr, ctx->g11.rowptr, ctx->k22,
-            ctx->pp11, ctx->g11.nnz, ctx->mu, ctx->N2, ctx->Nv, ctx->A, out);
+            ctx->pp11, ctx->g11.nnz, ctx->coef.p_mu, ctx->N2, ctx->Nv, ctx->A, out);
         LAUNCH_CHECK(ctx);
     } else {
         MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run first");

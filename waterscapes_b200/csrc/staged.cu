@@ -111,7 +111,8 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
                   const int32_t* __restrict__ rpA, const int32_t* __restrict__ colA,
                   const int32_t* __restrict__ rpB, const int32_t* __restrict__ colB,
                   const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                  int64_t n2, int64_t nv, const uint8_t* __restrict__ mask, const int* __restrict__ done) {
+                  int64_t n2, int64_t nv, const uint8_t* __restrict__ mask, const int* __restrict__ done,
+                  int contiguous) {
     if (done && *done) return;
     constexpr int kStages = CFG::kStages, NCW = CFG::kConsumers;
     using Stage = BlockStage<NR, blk_capv(CFG::kCapV, NR)>;
@@ -128,8 +129,16 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
     }
     __syncthreads();
 
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int nmine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+    // chunk order: interleaved over the CTAs, or one contiguous range per CTA (L1 reuse of the gathered
+    // vector entries between neighbouring rows)
+    int first = blockIdx.x, stride = gridDim.x;
+    int nmine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+    if (contiguous) {
+        const int per = nchunks / (int)gridDim.x, rem = nchunks % (int)gridDim.x;
+        first = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+        nmine = per + ((int)blockIdx.x < rem ? 1 : 0);
+        stride = 1;
+    }
 
     if (warp == 0) {
         // ------------------------------------------------ producer: one thread feeds the copy engine
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks)
 k_spmm_pipe(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __restrict__ rowptr,
             const int32_t* __restrict__ cols, const double* __restrict__ vals, const double* __restrict__ x,
             const double* __restrict__ b, double* __restrict__ out, double* __restrict__ d,
-            const double* __restrict__ dinv, double c1, double c2, const int* __restrict__ done) {
+            const double* __restrict__ dinv, double c1, double c2, const int* __restrict__ done, int contiguous) {
     if (done && *done) return;
     constexpr int kStages = CFG::kStages, NCW = CFG::kConsumers, GPW = 32 / LANES;
     using Stage = SpmmStage<CFG::kCap, CFG::kRows>;
@@ -308,8 +317,16 @@ k_spmm_pipe(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __
     }
     __syncthreads();
 
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int nmine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+    // chunk order: interleaved over the CTAs, or one contiguous range per CTA (L1 reuse of the gathered
+    // vector entries between neighbouring rows)
+    int first = blockIdx.x, stride = gridDim.x;
+    int nmine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+    if (contiguous) {
+        const int per = nchunks / (int)gridDim.x, rem = nchunks % (int)gridDim.x;
+        first = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+        nmine = per + ((int)blockIdx.x < rem ? 1 : 0);
+        stride = 1;
+    }
 
     if (warp == 0) {
         if (wl != 0) return;
@@ -423,25 +440,18 @@ k_spmm_pipe(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __
 // ------------------------------------------------------------------------------- configurations in use
 // Measured on B200 (profiles/r02_pipeline_sweep.md); MPET_BLK_CFG / MPET_SPM_CFG select another one
 // at plan-build time (development aid).
-using BlkCfg0 = BlkCfg<512, 4, 960, 2>;
-using BlkCfg1 = BlkCfg<1024, 8, 960, 1>;
-using BlkCfg2 = BlkCfg<512, 3, 1344, 2>;
-using BlkCfg3 = BlkCfg<512, 6, 640, 2>;
-using BlkCfg4 = BlkCfg<1024, 6, 1344, 1>;
-using BlkCfg5 = BlkCfg<384, 4, 960, 2>;
-constexpr int kNumBlkCfg = 6;
-constexpr int kBlkCapV[kNumBlkCfg] = {BlkCfg0::kCapV, BlkCfg1::kCapV, BlkCfg2::kCapV, BlkCfg3::kCapV, BlkCfg4::kCapV,
-                                      BlkCfg5::kCapV};
+using BlkCfg0 = BlkCfg<512, 4, 960, 2>;      // 2.03 ms on cfg5 (old design: 2.76 ms)
+using BlkCfg1 = BlkCfg<512, 3, 1344, 2>;     // 2.12 ms
+using BlkCfg2 = BlkCfg<384, 4, 960, 2>;      // 2.00 ms
+constexpr int kNumBlkCfg = 3;                // rejected: <1024,8,960,1> 2.63, <512,6,640,2> 2.81, <1024,6,1344,1> 2.29 ms
+constexpr int kBlkCapV[kNumBlkCfg] = {BlkCfg0::kCapV, BlkCfg1::kCapV, BlkCfg2::kCapV};
 
-using SpmCfg0 = SpmCfg<512, 4, 2048, 256, 2>;
-using SpmCfg1 = SpmCfg<1024, 8, 2048, 256, 1>;
-using SpmCfg2 = SpmCfg<256, 4, 1024, 128, 4>;
-using SpmCfg3 = SpmCfg<512, 6, 1344, 192, 2>;
-using SpmCfg4 = SpmCfg<384, 4, 2048, 256, 2>;     // 768 threads per SM: 85 registers, no spills in the W = 4 Chebyshev step
-using SpmCfg5 = SpmCfg<768, 8, 2048, 256, 1>;
-constexpr int kNumSpmCfg = 6;
-constexpr int kSpmCap[kNumSpmCfg] = {2048, 2048, 1024, 1344, 2048, 2048};
-constexpr int kSpmRows[kNumSpmCfg] = {256, 256, 128, 192, 256, 256};
+using SpmCfg0 = SpmCfg<384, 4, 2048, 256, 2>;    // 768 threads per SM: 85 registers, no spills in the W = 4 Chebyshev step
+using SpmCfg1 = SpmCfg<512, 4, 2048, 256, 2>;
+using SpmCfg2 = SpmCfg<384, 3, 1024, 128, 2>;    // small ring: most of the 228 KB stays L1 (no gain measured)
+constexpr int kNumSpmCfg = 3;
+constexpr int kSpmCap[kNumSpmCfg] = {2048, 2048, 1024};
+constexpr int kSpmRows[kNumSpmCfg] = {256, 256, 128};
 
 int env_cfg(const char* name, int n, int dflt) {
     const char* e = getenv(name);
@@ -470,7 +480,7 @@ void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, c
     }
     int grid = std::min(P.nchunks, CFG::kMinBlocks * ctx->sm_count);
     kern<<<grid, CFG::kThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x,
-                                            y, ctx->N2, ctx->Nv, mask, done);
+                                            y, ctx->N2, ctx->Nv, mask, done, env_cfg("MPET_BLK_ORDER", 2, 0));
     LAUNCH_CHECK(ctx);
 }
 
@@ -559,9 +569,6 @@ bool staged_block_spmv(mpet_ctx* ctx, const double* x, double* y, const uint8_t*
         case 0: return block_rows_cfg<BlkCfg0>(ctx, x, y, mask, done, st);
         case 1: return block_rows_cfg<BlkCfg1>(ctx, x, y, mask, done, st);
         case 2: return block_rows_cfg<BlkCfg2>(ctx, x, y, mask, done, st);
-        case 3: return block_rows_cfg<BlkCfg3>(ctx, x, y, mask, done, st);
-        case 4: return block_rows_cfg<BlkCfg4>(ctx, x, y, mask, done, st);
-        case 5: return block_rows_cfg<BlkCfg5>(ctx, x, y, mask, done, st);
         default: return false;
     }
 }
@@ -609,7 +616,8 @@ static void launch_spmm_pipe(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, 
         configured = true;
     }
     int grid = std::min(P.nchunks, CFG::kMinBlocks * ctx->sm_count);
-    kern<<<grid, CFG::kThreads, smem, st>>>(P.chunks, P.nchunks, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done);
+    kern<<<grid, CFG::kThreads, smem, st>>>(P.chunks, P.nchunks, M.rowptr, M.col, M.val, x, b, out, d, dinv, c1, c2, done,
+                                            env_cfg("MPET_SPM_ORDER", 2, 0));
     LAUNCH_CHECK(ctx);
 }
 
@@ -618,10 +626,19 @@ static void spmm_pipe_lanes(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, c
                             double* out, double* d, const double* dinv, double c1, double c2, const int* done,
                             cudaStream_t st) {
     const double mean = M.nrows > 0 ? (double)M.nnz / (double)M.nrows : 0.0;
-    if (mean > 40) launch_spmm_pipe<W, 32, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    else if (mean > 32) launch_spmm_pipe<W, 16, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    else if (mean > 5) launch_spmm_pipe<W, 8, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
-    else launch_spmm_pipe<W, 4, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st);
+    // lanes per row.  Measured on cfg5 (one preconditioner application, profiles/r01_pipeline_sweep.md): the
+    // kernels are bound by per-row work (shuffle reduction + epilogue), not by the gathers, so FEWER lanes win:
+    // P2 level (28 entries/row) 32 lanes 7.08 ms, 16: 5.06, 8: 4.33, 4: 3.33, 2: 3.41, 1: 3.70;
+    // P1 and aggregated levels (<= 20 entries/row) 8 lanes 3.49 ms, 4: 3.23, 2: 3.15, 1: 3.03.
+    // (development aid: MPET_SPM_LANES_HI / _LO override.)
+    int lanes = mean > 20 ? env_cfg("MPET_SPM_LANES_HI", 64, 2) : env_cfg("MPET_SPM_LANES_LO", 64, 1);
+    switch (lanes) {
+        case 1: launch_spmm_pipe<W, 1, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 2: launch_spmm_pipe<W, 2, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 8: launch_spmm_pipe<W, 8, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 16: launch_spmm_pipe<W, 16, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        default: launch_spmm_pipe<W, 4, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+    }
 }
 
 template <class CFG>
@@ -645,9 +662,6 @@ void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr&
     switch (P.cfg) {
         case 1: spmm_pipe_cfg<SpmCfg1>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
         case 2: spmm_pipe_cfg<SpmCfg2>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
-        case 3: spmm_pipe_cfg<SpmCfg3>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
-        case 4: spmm_pipe_cfg<SpmCfg4>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
-        case 5: spmm_pipe_cfg<SpmCfg5>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
         default: spmm_pipe_cfg<SpmCfg0>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
     }
 }

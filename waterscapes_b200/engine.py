@@ -90,6 +90,13 @@ class Engine:
         self._ck(self.lib.mpet_set_params(self._ctx, float(E), float(nu), arr(alpha, A), arr(K, A),
                                           arr(S, A * A), arr(c, A), float(dt), float(theta)))
 
+    def set_params_total_pressure(self, E, nu, alpha, K, S, c, dt, theta):
+        """Total-pressure formulation: the mesh was set with J + 1 P1 fields (field 0 = total pressure)."""
+        J = self.sizes["A"] - 1
+        arr = lambda v, n: (C.c_double * max(n, 1))(*[float(x) for x in np.asarray(v, dtype=float).ravel()])
+        self._ck(self.lib.mpet_set_params_total_pressure(self._ctx, float(E), float(nu), arr(alpha, J), arr(K, J),
+                                                         arr(S, J * J), arr(c, J), float(dt), float(theta)))
+
     def assemble_lhs(self):
         self._ck(self.lib.mpet_assemble_lhs(self._ctx, self._stream()))
 

@@ -75,9 +75,19 @@ class MPETSolver(object):
         params.add("krylov_maxit", 10000)
         return params
 
+    # sub-space index of network i in the mixed space (0 is the displacement) and number of P1 fields;
+    # the total-pressure solver shifts both by one (its sub-space 1 is the total pressure)
+    _first_network_sub = 1
+
+    def _num_p1_fields(self):
+        return int(self.problem.params["J"])
+
+    def _net_sub(self, i):
+        return i + self._first_network_sub
+
     def create_function_spaces(self, mesh):
         "Mixed space [P2]^3 x [P1]^J; the dof map and sparsity graph are built on the device."
-        J = int(self.problem.params["J"])
+        J = self._num_p1_fields()
         if self.engine.sizes is None:
             self.engine.set_mesh(mesh.coordinates, mesh.cells, J)
         return FunctionSpace(mesh, J, self.engine)
@@ -124,10 +134,13 @@ class MPETSolver(object):
                 [[_f(v) for v in row] for row in p["S"]], [_f(v) for v in p["c"]], float(self.dt),
                 float(self.params["theta"]))
         if getattr(self, "_pushed", None) != vals:
-            self.engine.set_params(*vals)
+            self._engine_set_params(*vals)
             self._pushed = vals
             self._pc_dirty = True
         return J
+
+    def _engine_set_params(self, *vals):
+        self.engine.set_params(*vals)
 
     def _exchange_is_symmetric(self):
         S = np.array([[_f(v) for v in row] for row in self.problem.params["S"]], dtype=float)
@@ -184,6 +197,57 @@ class MPETSolver(object):
             vals = torch.as_tensor(np.asarray(coef.eval_points(pts), dtype=float), device=y.device)
             self.engine.mass_apply(space, scale, vals, y)
 
+    # ------------------------------------------------------------------ pieces of the forms
+    def _robin_entries(self, i):
+        """-dt*theta*beta_i int_{marker 2} p_i q_i ds as unique (row, col, value) triplets
+        (mpetsolver.py:252-253; lhs(L2[i]) in mpettotalpressuresolver.py:323)."""
+        sp = self.VQ
+        dt, theta = float(self.dt), float(self.params["theta"])
+        op = self._facet_op("c", i, ROBIN_MARKER, False)
+        beta = float(self.problem.beta[i])
+        if op.nf == 0 or beta == 0.0:
+            return RobinEntries(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
+        lo, _ = sp.sub_range(self._net_sub(i))
+        rows = np.repeat(op.nodes[:, :, None], 3, axis=2).ravel() + lo
+        cols = np.repeat(op.nodes[:, None, :], 3, axis=1).ravel() + lo
+        vals = (-dt * theta * beta * op.area[:, None, None] * _M3[None]).ravel()
+        key = rows * sp.N + cols
+        uk, inv = np.unique(key, return_inverse=True)
+        acc = np.zeros(uk.shape[0])
+        np.add.at(acc, inv, vals)
+        return RobinEntries((uk // sp.N).astype(np.int32), (uk % sp.N).astype(np.int32), acc)
+
+    def _load_sources(self, i, b):
+        """b += dt*int g_i q dx + dt*int_{marker 1} I_i q ds on network i's rows (mpetsolver.py:249)."""
+        sp, eng = self.VQ, self.engine
+        dt = float(self.dt)
+        lo, hi = sp.sub_range(self._net_sub(i))
+        y = b[lo:hi]
+        self._cell_load(self.problem.g[i], 1, y, dt)
+        if not _is_zero(self.problem.I[i]):
+            op = self._facet_op("c", i, NEUMANN_MARKER, False)
+            if op.nf:
+                op.apply(eng, op.data(self.problem.I[i]), y, scale=dt)
+
+    def _load_robin_rhs(self, i, b):
+        """b += dt*beta_i int_{marker 2} ((1-theta) p_i^- - p_robin_i) q ds (mpetsolver.py:254;
+        rhs(L2[i]) in mpettotalpressuresolver.py:323)."""
+        sp, eng = self.VQ, self.engine
+        dt, theta = float(self.dt), float(self.params["theta"])
+        beta = float(self.problem.beta[i])
+        if beta == 0.0:
+            return
+        op = self._facet_op("c", i, ROBIN_MARKER, False)
+        if not op.nf:
+            return
+        lo, hi = sp.sub_range(self._net_sub(i))
+        y = b[lo:hi]
+        if not _is_zero(self.problem.p_robin[i]):
+            op.apply(eng, op.data(self.problem.p_robin[i]), y, scale=-dt * beta)
+        if theta != 1.0:
+            pprev = self.up_.x[lo:hi][torch.as_tensor(op.nodes.ravel(), device=eng.device)]
+            eng.csr_spmv(op.csr[0], op.csr[1], op.csr[2], (dt * beta * (1.0 - theta)) * pprev, y, beta=1.0)
+
     # ------------------------------------------------------------------ assemble(form)
     def _assemble(self, form):
         eng = self.engine
@@ -198,42 +262,13 @@ class MPETSolver(object):
             self._ensure_prec()
             return Matrix(self, "P")
         if kind == "a_robin":
-            i = form.index
-            op = self._facet_op("c", i, ROBIN_MARKER, False)
-            beta = float(self.problem.beta[i])
-            if op.nf == 0 or beta == 0.0:
-                return RobinEntries(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
-            lo, _ = sp.sub_range(i + 1)
-            rows = np.repeat(op.nodes[:, :, None], 3, axis=2).ravel() + lo
-            cols = np.repeat(op.nodes[:, None, :], 3, axis=1).ravel() + lo
-            vals = (-dt * theta * beta * op.area[:, None, None] * _M3[None]).ravel()
-            key = rows * sp.N + cols
-            uk, inv = np.unique(key, return_inverse=True)
-            acc = np.zeros(uk.shape[0])
-            np.add.at(acc, inv, vals)
-            return RobinEntries((uk // sp.N).astype(np.int32), (uk % sp.N).astype(np.int32), acc)
+            return self._robin_entries(form.index)
         b = torch.zeros(sp.N, dtype=torch.float64, device=eng.device)
         if kind == "L":
             eng.rhs_prev(self.up_.x, b)
         elif kind == "L1":
-            i = form.index
-            lo, hi = sp.sub_range(i + 1)
-            y = b[lo:hi]
-            self._cell_load(self.problem.g[i], 1, y, dt)
-            if not _is_zero(self.problem.I[i]):
-                op = self._facet_op("c", i, NEUMANN_MARKER, False)
-                if op.nf:
-                    op.apply(eng, op.data(self.problem.I[i]), y, scale=dt)
-            beta = float(self.problem.beta[i])
-            if beta != 0.0:
-                op = self._facet_op("c", i, ROBIN_MARKER, False)
-                if op.nf:
-                    if not _is_zero(self.problem.p_robin[i]):
-                        op.apply(eng, op.data(self.problem.p_robin[i]), y, scale=-dt * beta)
-                    if theta != 1.0:
-                        pprev = self.up_.x[lo:hi][torch.as_tensor(op.nodes.ravel(), device=eng.device)]
-                        eng.csr_spmv(op.csr[0], op.csr[1], op.csr[2],
-                                     (dt * beta * (1.0 - theta)) * pprev, y, beta=1.0)
+            self._load_sources(form.index, b)
+            self._load_robin_rhs(form.index, b)
         elif kind == "L0":
             f, s = self.problem.f, self.problem.s
             if isinstance(f, Constant):
