@@ -33,7 +33,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)
-    ap.add_argument("--n", type=int, default=None, help="override the mesh resolution of the config")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=None, help="override the mesh resolution of the config")
     ap.add_argument("--rtol", type=float, default=1e-6,
                     help="Krylov tolerance (reference authors' intent: sandbox/2D_1net_totalpressure.py:168-170)")
     ap.add_argument("--maxit", type=int, default=10000)
