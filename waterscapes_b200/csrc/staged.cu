@@ -9,7 +9,7 @@
 // memory.  The only long-latency operation left in a consumer is the 256-bit gather of the neighbour's
 // vector entries.
 //
-// Pipeline (second design, profiles/r02_block_rows_barrier.md): every stage has a `full` mbarrier
+// Pipeline (second design, profiles/r01_block_rows_staged_v1.md): every stage has a `full` mbarrier
 // (producer's expect_tx + the copy engine's complete_tx) and an `empty` mbarrier (one arrival per consumer
 // warp).  There is no CTA-wide barrier in the steady state: the first design ended every chunk with
 // __syncthreads and ncu attributed 39 % of all stall samples to it, because a chunk holds fewer rows than
@@ -438,7 +438,7 @@ k_spmm_pipe(const SpmmChunk* __restrict__ chunks, int nchunks, const int32_t* __
 }
 
 // ------------------------------------------------------------------------------- configurations in use
-// Measured on B200 (profiles/r02_pipeline_sweep.md); MPET_BLK_CFG / MPET_SPM_CFG select another one
+// Measured on B200 (profiles/r01_pipeline_sweep.md); MPET_BLK_CFG / MPET_SPM_CFG select another one
 // at plan-build time (development aid).
 using BlkCfg0 = BlkCfg<512, 4, 960, 2>;      // 2.03 ms on cfg5 (old design: 2.76 ms)
 using BlkCfg1 = BlkCfg<512, 3, 1344, 2>;     // 2.12 ms
