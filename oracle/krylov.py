@@ -18,6 +18,15 @@ import scipy.sparse as sp
 
 CHEB_DEGREE = 2
 CHEB_RATIO = 4.0
+# well-conditioned blocks (cond(D^-1 A) <= POLY_KAPPA_MAX, e.g. the mass-dominated network blocks) are inverted
+# by a Chebyshev polynomial on the WHOLE spectrum instead of a V-cycle (amg.cu: same constants)
+POLY_KAPPA_MAX = 12.0
+POLY_TARGET = 1.0e-4
+POLY_MAX_DEGREE = 16
+LANCZOS_STEPS = 40
+# P1-field blocks that keep a hierarchy: P1_CYCLES stationary cycles, Chebyshev degree P1_DEGREE (amg.cu)
+P1_CYCLES = 2
+P1_DEGREE = 4
 COARSE_MAX = 300
 DENSE_MAX = 700
 MAX_LEVELS = 12
@@ -158,12 +167,60 @@ class _Level:
     pass
 
 
+def lanczos_bounds(A, dinv, steps=LANCZOS_STEPS):
+    """Extreme Ritz values of D^-1 A from `steps` Lanczos steps in the D inner product, deterministic start
+    vector (amg.cu:lanczos_bounds runs the same recurrence on the device)."""
+    n = A.shape[0]
+    d = 1.0 / dinv
+    i = np.arange(n)
+    v = 1.0 + 0.5 * np.sin(0.37 * i + 0.1 * (i % 7))
+    v = v / np.sqrt(np.sum(d * v * v))
+    v_prev = np.zeros(n)
+    beta = 0.0
+    al, be = [], []
+    for _ in range(min(steps, n)):
+        w = dinv * (A @ v)
+        a = float(np.sum(d * w * v))
+        w = w - a * v - beta * v_prev
+        al.append(a)
+        b2 = float(np.sum(d * w * w))
+        if b2 <= 1e-28 * max(1.0, a * a):
+            break
+        beta = np.sqrt(b2)
+        be.append(beta)
+        v_prev, v = v, w / beta
+    m = len(al)
+    T = np.diag(al) + np.diag(be[:m - 1], 1) + np.diag(be[:m - 1], -1)
+    ev = np.linalg.eigvalsh(T)
+    return float(ev[0]), float(ev[-1])
+
+
+def poly_degree(lo, hi):
+    """Smallest Chebyshev degree whose residual polynomial is below POLY_TARGET on [lo, hi]."""
+    kappa = hi / lo
+    sigma = (np.sqrt(kappa) - 1.0) / (np.sqrt(kappa) + 1.0)
+    k = 1
+    while k < POLY_MAX_DEGREE and 2.0 * sigma ** k / (1.0 + sigma ** (2 * k)) > POLY_TARGET:
+        k += 1
+    return k
+
+
 class ScalarAMG:
     """V-cycle hierarchy for one scalar SPD block (identity rows on eliminated Dirichlet dofs)."""
 
-    def __init__(self, A0, first_coarse=None):
+    def __init__(self, A0, first_coarse=None, allow_polynomial=False, cycles=1, degree=None):
         self.levels = []
+        self.poly = None
+        self.cycles = cycles
+        self.degree = CHEB_DEGREE if degree is None else degree
         self._push(A0.tocsr(), None)
+        self.coarse_inv = None
+        if allow_polynomial:
+            lmin, lmax = lanczos_bounds(self.levels[0].A, self.levels[0].dinv)
+            lo, hi = 0.97 * lmin, 1.02 * lmax
+            if lmin > 0 and hi / lo <= POLY_KAPPA_MAX:
+                self.poly = (lo, hi, poly_degree(lo, hi))
+                return
         if first_coarse is not None:
             P, A1 = first_coarse
             self._push(A1.tocsr(), P.tocsr())
@@ -203,13 +260,13 @@ class ScalarAMG:
         L.lmax = gersh if (est <= 0 or est > gersh) else est
         self.levels.append(L)
 
-    def _cheb(self, L, b, x):
-        lmax, lmin = L.lmax, L.lmax / CHEB_RATIO
+    def _cheb(self, L, b, x, bounds=None, degree=None):
+        lmax, lmin = (L.lmax, L.lmax / CHEB_RATIO) if bounds is None else (bounds[1], bounds[0])
         theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
         sigma = theta / delta
         rho_old = 1.0 / sigma
         d = None
-        for k in range(CHEB_DEGREE):
+        for k in range(self.degree if degree is None else degree):
             if k == 0:
                 r = b if x is None else b - L.A @ x
                 d = (1.0 / theta) * (L.dinv[:, None] * r)
@@ -238,7 +295,13 @@ class ScalarAMG:
     def apply(self, B):
         """B: [n, nrhs] -> approximate A^-1 B."""
         B = B.reshape(B.shape[0], -1)
-        return self._vcycle(0, B)
+        if self.poly is not None:
+            lo, hi, deg = self.poly
+            return self._cheb(self.levels[0], B, None, bounds=(lo, hi), degree=deg)
+        x = self._vcycle(0, B)
+        for _ in range(1, self.cycles):          # stationary iteration x <- x + B (b - A x)
+            x = x + self._vcycle(0, B - self.levels[0].A @ x)
+        return x
 
 
 def _eliminate(M, mask):
@@ -255,7 +318,8 @@ def _eliminate(M, mask):
 
 class BlockAMG:
     """Block-diagonal preconditioner: shared scalar P2 block mu*(grad,grad) for the three displacement
-    components (p-coarsened to P1, then aggregation) + one P1 block per network."""
+    components (p-coarsened to P1, then aggregation) + one hierarchy per P1 field, which degenerates to a
+    Chebyshev polynomial on the whole spectrum when the field's block is well conditioned (amg.cu)."""
 
     def __init__(self, oracle, dirichlet_dofs):
         o = oracle
@@ -290,7 +354,8 @@ class BlockAMG:
         self.p = []
         for i in range(A):
             d = sp_.p_dofs(i)
-            self.p.append(ScalarAMG(_eliminate(P[d][:, d], mask[d])))
+            self.p.append(ScalarAMG(_eliminate(P[d][:, d], mask[d]), allow_polynomial=True, cycles=P1_CYCLES,
+                                    degree=P1_DEGREE))
         self.N2, self.Nv, self.A = N2, Nv, A
 
     def __call__(self, r):

@@ -1,5 +1,6 @@
 """Scale probe: timings of each phase of the hot path on one GPU (development aid)."""
-import sys, time
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from waterscapes_b200.workloads import make_problem, sizes
 from waterscapes_b200.mpet import MPETSolver

@@ -205,6 +205,69 @@ k_masked_copy(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* 
     }
 }
 
+// pattern of diag(B_0, .., B_{A-1}) for A blocks that share the vertex graph g11
+__global__ void k_blockdiag_pattern(const int32_t* __restrict__ rp11, const int32_t* __restrict__ col11, int64_t nv,
+                                    int64_t nnz11, int A, int32_t* __restrict__ rp, int32_t* __restrict__ col) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t <= (int64_t)A * nv) {
+        const int64_t i = t / nv, v = t - i * nv;
+        rp[t] = (int32_t)((i < A) ? i * nnz11 + rp11[v] : (int64_t)A * nnz11);
+    }
+    if (t < (int64_t)A * nnz11) {
+        const int64_t i = t / nnz11, e = t - i * nnz11;
+        col[t] = (int32_t)(i * nv + col11[e]);
+    }
+}
+
+// ---- Lanczos in the D inner product (setup only): deterministic single-block reductions
+__global__ void __launch_bounds__(1024)
+k_lz_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ dinv,
+         const uint8_t* __restrict__ own, double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024)
+        if (!own || own[i]) s += x[i] * y[i] / dinv[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+__global__ void k_lz_start(int64_t n, double* __restrict__ v, double* __restrict__ vprev) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    v[i] = 1.0 + 0.5 * sin(0.37 * (double)i + 0.1 * (double)(i % 7));
+    vprev[i] = 0.0;
+}
+__global__ void k_lz_scale(int64_t n, double* __restrict__ v, double s) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= s;
+}
+// w = dinv * w - alpha * v - beta * vprev
+__global__ void k_lz_update(int64_t n, double* __restrict__ w, const double* __restrict__ dinv, const double* __restrict__ v,
+                            const double* __restrict__ vprev, double alpha, double beta, int scale_first) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = scale_first ? dinv[i] * w[i] : w[i];
+    w[i] = t - alpha * v[i] - beta * vprev[i];
+}
+// vprev = v ; v = w / beta
+__global__ void k_lz_next(int64_t n, const double* __restrict__ w, double inv_beta, double* __restrict__ v,
+                          double* __restrict__ vprev) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vprev[i] = v[i];
+    v[i] = w[i] * inv_beta;
+}
+
+__global__ void k_add_inplace(int64_t n, const double* __restrict__ e, double* __restrict__ x, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) x[i] += e[i];
+}
+
 __global__ void k_gershgorin(int64_t nrows, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
                              const double* __restrict__ dinv, double* __restrict__ out) {
     int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -451,6 +514,18 @@ std::vector<double> dense_inverse(const HostCsr& A) {
 
 // =============================================================================== hierarchy
 const int kChebDegree = 2;
+// well-conditioned blocks (cond(D^-1 A) <= kPolyKappaMax, e.g. mass-dominated network blocks) are inverted by a
+// Chebyshev polynomial on the WHOLE spectrum instead of a V-cycle (oracle/krylov.py: same constants)
+const double kPolyKappaMax = 12.0;
+const double kPolyTarget = 1.0e-4;
+const int kPolyMaxDegree = 16;
+const int kLanczosSteps = 40;
+// P1-field blocks that keep a hierarchy are applied as kP1Cycles stationary cycles with degree-kP1Degree Chebyshev
+// smoothing.  MINRES on the MPET system is very sensitive to the accuracy of these (cheap) blocks; measured on
+// cfg5 (iterations / ms per step): 1 cycle, degree 2: 549 / 2892; degree 4: 469 / 2522; 2 cycles: 406 / 2214;
+// 3 cycles: 350 / 1989; 2 cycles, degree 4: 341 / 1942; 4 cycles: 340 / 1995 (plateau = exact block solves).
+const int kP1Cycles = 2;
+const int kP1Degree = 4;
 const double kChebRatio = 4.0;    // smooth the upper [lambda_max / ratio, lambda_max] of D^-1 A
 const int64_t kCoarseMax = 300;
 const int kMaxLevels = 12;
@@ -492,17 +567,22 @@ void launch_plain(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const do
 }
 
 // Chebyshev smoothing on level L: x_out = S(b, x_in); x_in == nullptr means zero initial guess.
+static int g_p_degree() {
+    static const int d = []() { const char* e = getenv("MPET_P_DEGREE"); return e ? std::max(1, atoi(e)) : kP1Degree; }();
+    return d;
+}
+
 template <int W>
 void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, double* x_out, const int* done,
-               cudaStream_t st) {
+               cudaStream_t st, double lo = 0.0, double hi = 0.0, int degree = 0) {
     const int64_t n = L.A.nrows;
-    const double lmax = L.lambda_max, lmin = lmax / kChebRatio;
+    const double lmax = degree > 0 ? hi : L.lambda_max, lmin = degree > 0 ? lo : lmax / kChebRatio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
     const double sigma = theta / delta;
     double rho_old = 1.0 / sigma;
     double* buf[2] = {L.x, L.t};
     const double* cur = x_in;
-    const int steps = kChebDegree;
+    const int steps = degree > 0 ? degree : (W == 1 ? g_p_degree() : kChebDegree);
     for (int k = 0; k < steps; ++k) {
         bool last = (k == steps - 1);
         double* dst = last ? x_out : buf[k & 1];
@@ -532,6 +612,10 @@ template <int W>
 void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x, const int* done, cudaStream_t st) {
     AmgLevel& L = H.levels[lev];
     const int64_t n = L.A.nrows;
+    if (H.poly_degree > 0) {       // polynomial mode: no hierarchy
+        chebyshev<W>(ctx, L, b, nullptr, x, done, st, H.poly_lo, H.poly_hi, H.poly_degree);
+        return;
+    }
     if (lev == (int)H.levels.size() - 1) {
         if (H.coarse_inv) {
             k_dense_apply<W><<<grid_for((int64_t)n * 32, 256), 256, 0, st>>>((int)n, H.coarse_inv, b, x, done);
@@ -618,6 +702,96 @@ double estimate_lambda_max(mpet_ctx* ctx, AmgLevel& L, cudaStream_t st) {
     return est;
 }
 
+// smallest / largest eigenvalue of a symmetric tridiagonal matrix (diagonal a, off-diagonal b) by Sturm bisection
+static void tridiag_extremes(const std::vector<double>& a, const std::vector<double>& b, double& emin, double& emax) {
+    const int m = (int)a.size();
+    double lo = a[0], hi = a[0];
+    for (int i = 0; i < m; ++i) {
+        const double r = (i > 0 ? std::fabs(b[i - 1]) : 0.0) + (i + 1 < m ? std::fabs(b[i]) : 0.0);
+        lo = std::min(lo, a[i] - r);
+        hi = std::max(hi, a[i] + r);
+    }
+    auto count_below = [&](double x) {      // number of eigenvalues < x
+        int cnt = 0;
+        double q = a[0] - x;
+        if (q < 0) ++cnt;
+        for (int i = 1; i < m; ++i) {
+            const double den = (q == 0.0) ? 1e-300 : q;
+            q = a[i] - x - b[i - 1] * b[i - 1] / den;
+            if (q < 0) ++cnt;
+        }
+        return cnt;
+    };
+    auto kth = [&](int k) {                 // k-th smallest eigenvalue, k = 0 .. m-1
+        double l = lo, h = hi;
+        for (int it = 0; it < 200; ++it) {
+            const double mid = 0.5 * (l + h);
+            if (count_below(mid) <= k) l = mid; else h = mid;
+            if (h - l <= 1e-15 * std::max(1.0, std::fabs(h))) break;
+        }
+        return 0.5 * (l + h);
+    };
+    emin = kth(0);
+    emax = kth(m - 1);
+}
+
+// Extreme Ritz values of D^-1 A after kLanczosSteps Lanczos steps in the D inner product (deterministic start
+// vector, fixed-order reductions; multi-GPU: ghost refresh before every product, owned rows in the sums,
+// all-reduced).  oracle/krylov.py:lanczos_bounds is the same recurrence.
+void lanczos_bounds(mpet_ctx* ctx, AmgLevel& L, const uint8_t* own_dev, double& lmin, double& lmax, cudaStream_t st) {
+    const int64_t n = L.A.nrows;
+    double *v = nullptr, *vp = nullptr, *w = nullptr, *sc = nullptr;
+    CUDA_CHECK(cudaMalloc(&v, sizeof(double) * n));
+    CUDA_CHECK(cudaMalloc(&vp, sizeof(double) * n));
+    CUDA_CHECK(cudaMalloc(&w, sizeof(double) * n));
+    CUDA_CHECK(cudaMalloc(&sc, sizeof(double)));
+    auto dot = [&](const double* x, const double* y) {
+        k_lz_dot<<<1, 1024, 0, st>>>(n, x, y, L.dinv, own_dev, sc);
+        LAUNCH_CHECK(ctx);
+        dist_allreduce_sum(ctx, sc, 1, st);
+        double h = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&h, sc, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        return h;
+    };
+    const int g = grid_for(n, 256);
+    k_lz_start<<<g, 256, 0, st>>>(n, v, vp);
+    LAUNCH_CHECK(ctx);
+    if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, v, false, nullptr, st);
+    k_lz_scale<<<g, 256, 0, st>>>(n, v, 1.0 / std::sqrt(dot(v, v)));
+    LAUNCH_CHECK(ctx);
+    std::vector<double> al, be;
+    double beta = 0.0;
+    for (int j = 0; j < kLanczosSteps && j < n; ++j) {
+        launch_plain<1>(ctx, L.A, SpmmPlan(), v, w, 0.0, nullptr, st);
+        k_lz_update<<<g, 256, 0, st>>>(n, w, L.dinv, v, vp, 0.0, 0.0, 1);          // w = D^-1 A v
+        LAUNCH_CHECK(ctx);
+        const double a = dot(w, v);
+        k_lz_update<<<g, 256, 0, st>>>(n, w, L.dinv, v, vp, a, beta, 0);            // w -= a v + beta v_prev
+        LAUNCH_CHECK(ctx);
+        al.push_back(a);
+        const double b2 = dot(w, w);
+        if (b2 <= 1e-28 * std::max(1.0, a * a)) break;
+        beta = std::sqrt(b2);
+        be.push_back(beta);
+        k_lz_next<<<g, 256, 0, st>>>(n, w, 1.0 / beta, v, vp);
+        LAUNCH_CHECK(ctx);
+        if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, v, false, nullptr, st);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    be.resize(al.size() > 0 ? al.size() - 1 : 0);
+    tridiag_extremes(al, be, lmin, lmax);
+    cudaFree(v); cudaFree(vp); cudaFree(w); cudaFree(sc);
+}
+
+int poly_degree_for(double lo, double hi) {
+    const double kappa = hi / lo;
+    const double sigma = (std::sqrt(kappa) - 1.0) / (std::sqrt(kappa) + 1.0);
+    int k = 1;
+    while (k < kPolyMaxDegree && 2.0 * std::pow(sigma, k) / (1.0 + std::pow(sigma, 2 * k)) > kPolyTarget) ++k;
+    return k;
+}
+
 void compute_dinv_host(mpet_ctx* ctx, AmgLevel& L, const HostCsr& H) {
     std::vector<double> d(H.nrows, 1.0);
     for (int64_t r = 0; r < H.nrows; ++r)
@@ -653,7 +827,15 @@ HostCsr distributed_transition(mpet_ctx* ctx, AmgHierarchy& H, int W, cudaStream
     AmgLevel& F = H.levels.back();
     HostCsr A = download(F.A);
     const int64_t n = A.nrows;
-    const std::vector<uint8_t>& ownn = dist_own_nodes(ctx);     // vertices are the first n nodes
+    // level vectors are nblocks vertex fields (1, or the A fields of the merged pressure hierarchy)
+    const int64_t nblocks = n / ctx->Nv;
+    MPET_REQUIRE(nblocks * ctx->Nv == n, "distributed transition level is not a multiple of the vertex count");
+    const int halo_w1 = nblocks == 1 ? DIST_PLAN_P1W1 : DIST_PLAN_P1WA;
+    std::vector<uint8_t> ownn((size_t)n);
+    {
+        const std::vector<uint8_t>& on = dist_own_nodes(ctx);   // vertices are the first Nv nodes
+        for (int64_t i = 0; i < n; ++i) ownn[i] = on[i % ctx->Nv];
+    }
     const int rank = dist_rank(ctx), nr = dist_nranks(ctx);
     std::vector<int32_t> l2o(n, -1), o2l;
     for (int64_t i = 0; i < n; ++i)
@@ -691,7 +873,7 @@ HostCsr distributed_transition(mpet_ctx* ctx, AmgHierarchy& H, int W, cudaStream
     double* dg = nullptr;
     CUDA_CHECK(cudaMalloc(&dg, sizeof(double) * n));
     CUDA_CHECK(cudaMemcpy(dg, g.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
-    dist_halo(ctx, DIST_PLAN_P1W1, dg, false, nullptr, st);
+    dist_halo(ctx, halo_w1, dg, false, nullptr, st);
     CUDA_CHECK(cudaMemcpyAsync(g.data(), dg, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     cudaFree(dg);
@@ -813,6 +995,11 @@ void make_plan(mpet_ctx* ctx, const DevCsr& M, SpmmPlan& plan) {
 }
 
 void finish_hierarchy(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
+    if (getenv("MPET_AMG_VERBOSE")) {
+        fprintf(stderr, "[mpet amg] hierarchy W=%d:", H.nrhs);
+        for (auto& L : H.levels) fprintf(stderr, " %lld rows/%lld nnz", (long long)L.A.nrows, (long long)L.A.nnz);
+        fprintf(stderr, " | coarse %s (%lld)\n", H.coarse_inv ? "dense inverse" : "Chebyshev", (long long)H.levels.back().A.nrows);
+    }
     for (auto& L : H.levels) {
         alloc_level_work(ctx, L, H.nrhs);
         L.lambda_max = estimate_lambda_max(ctx, L, st);
@@ -908,7 +1095,15 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         finish_hierarchy(ctx, *H, st);
         ctx->amg_u = H;
     }
-    // ---- pressure blocks
+    // ---- P1 fields: one hierarchy per field.  (Merging the fields into one block-diagonal hierarchy was tried:
+    // one third of the launches, but the shared Chebyshev interval / prolongator damping cost 11 % more MINRES
+    // iterations on cfg5 -- 614 vs 552 -- for the same time per iteration.)
+    uint8_t* own_dev = nullptr;
+    if (dist_active(ctx) && A > 0) {
+        const std::vector<uint8_t>& on = dist_own_nodes(ctx);
+        own_dev = dev_alloc<uint8_t>(ctx, nv);
+        CUDA_CHECK(cudaMemcpy(own_dev, on.data(), (size_t)nv, cudaMemcpyHostToDevice));
+    }
     for (int i = 0; i < A; ++i) {
         AmgHierarchy* H = new AmgHierarchy();
         H->nrhs = 1;
@@ -917,20 +1112,57 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
                             ctx->bc_mask + 3 * n2 + (int64_t)i * nv, &L0.dinv, st);
         if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P1W1;
         H->levels.push_back(L0);
-        extend_by_aggregation(ctx, *H, st);
+        // spectrum of D^-1 A: a small condition number (mass-dominated field) is inverted far more accurately --
+        // and cheaper -- by a Chebyshev polynomial on the whole spectrum than by a V-cycle, and MINRES on this
+        // system is very sensitive to the accuracy of the P1 blocks.
+        double lmin = 0, lmax = 0;
+        lanczos_bounds(ctx, H->levels[0], own_dev, lmin, lmax, st);
+        const double lo = 0.97 * lmin, hi = 1.02 * lmax;
+        if (lmin > 0 && hi / lo <= kPolyKappaMax && !getenv("MPET_NO_POLY")) {
+            H->poly_degree = poly_degree_for(lo, hi);
+            H->poly_lo = lo;
+            H->poly_hi = hi;
+        } else {
+            extend_by_aggregation(ctx, *H, st);
+        }
+        if (getenv("MPET_AMG_VERBOSE"))
+            fprintf(stderr, "[mpet amg] P1 field %d: D^-1 A spectrum [%.4f, %.4f] -> %s (degree %d)\n", i, lmin, lmax,
+                    H->poly_degree ? "Chebyshev polynomial" : "V-cycle", H->poly_degree);
         finish_hierarchy(ctx, *H, st);
         ctx->amg_p[i] = H;
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// k cycles per application = the symmetric stationary iteration x <- x + B (b - A x) started from zero
+// (kP1Cycles for the P1 fields, 1 for the displacement block; development aid: MPET_P_CYCLES / MPET_U_CYCLES)
+template <int W>
+static void cycles(mpet_ctx* ctx, AmgHierarchy& H, int ncycles, const double* b, double* x, const int* done,
+                   cudaStream_t st) {
+    vcycle<W>(ctx, H, 0, b, x, done, st);
+    AmgLevel& L = H.levels[0];
+    for (int c = 1; c < ncycles; ++c) {
+        if (!H.cyc_r) {
+            H.cyc_r = dev_alloc<double>(ctx, L.A.nrows * W);
+            H.cyc_e = dev_alloc<double>(ctx, L.A.nrows * W);
+        }
+        launch_epi<W, EPI_RESID>(ctx, L.A, L.planA, x, b, H.cyc_r, nullptr, nullptr, 0, 0, done, st);
+        if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, H.cyc_r, false, done, st);
+        vcycle<W>(ctx, H, 0, H.cyc_r, H.cyc_e, done, st);
+        k_add_inplace<<<grid_for(L.A.nrows * W, 256), 256, 0, st>>>(L.A.nrows * W, H.cyc_e, x, done);
+        LAUNCH_CHECK(ctx);
+    }
+}
+
 // r, z in the solver-internal layout (layout.cuh).  The block-diagonal preconditioner is A + 1 independent
-// V-cycles; on one GPU the per-network cycles (dozens of small launches each) run on their own high-priority
+// cycles; on one GPU the per-field cycles (dozens of small launches each) run on their own high-priority
 // streams beside the displacement cycle and join before returning.  Multi-GPU keeps one stream: the halo
 // exchanges of all cycles share one NCCL communicator and must be issued in one order on every rank.
 void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
     static const bool want_streams = []() { const char* e = getenv("MPET_PC_STREAMS"); return !(e && e[0] == '0'); }();
+    static const int p_cycles = []() { const char* e = getenv("MPET_P_CYCLES"); return e ? std::max(1, atoi(e)) : kP1Cycles; }();
+    static const int u_cycles = []() { const char* e = getenv("MPET_U_CYCLES"); return e ? std::max(1, atoi(e)) : 1; }();
     const bool fork = want_streams && ctx->A > 0 && !dist_active(ctx);
     if (fork) {
         if (ctx->pc_streams_ready < ctx->A) {
@@ -946,18 +1178,20 @@ void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaS
         CUDA_CHECK(cudaEventRecord(ctx->pc_fork, st));
         for (int i = 0; i < ctx->A; ++i) {
             const int64_t off = 4 * n2 + (int64_t)i * nv;
+            AmgHierarchy& H = *ctx->amg_p[i];
             CUDA_CHECK(cudaStreamWaitEvent(ctx->pc_stream[i], ctx->pc_fork, 0));
-            vcycle<1>(ctx, *ctx->amg_p[i], 0, r + off, z + off, done, ctx->pc_stream[i]);
+            cycles<1>(ctx, H, H.poly_degree ? 1 : p_cycles, r + off, z + off, done, ctx->pc_stream[i]);
             CUDA_CHECK(cudaEventRecord(ctx->pc_join[i], ctx->pc_stream[i]));
         }
-        vcycle<4>(ctx, *ctx->amg_u, 0, r, z, done, st);
+        cycles<4>(ctx, *ctx->amg_u, u_cycles, r, z, done, st);
         for (int i = 0; i < ctx->A; ++i) CUDA_CHECK(cudaStreamWaitEvent(st, ctx->pc_join[i], 0));
         return;
     }
-    vcycle<4>(ctx, *ctx->amg_u, 0, r, z, done, st);
+    cycles<4>(ctx, *ctx->amg_u, u_cycles, r, z, done, st);
     for (int i = 0; i < ctx->A; ++i) {
-        int64_t off = 4 * n2 + (int64_t)i * nv;
-        vcycle<1>(ctx, *ctx->amg_p[i], 0, r + off, z + off, done, st);
+        const int64_t off = 4 * n2 + (int64_t)i * nv;
+        AmgHierarchy& H = *ctx->amg_p[i];
+        cycles<1>(ctx, H, H.poly_degree ? 1 : p_cycles, r + off, z + off, done, st);
     }
 }
 

@@ -14,6 +14,7 @@
 // materialised in HBM.
 #include "ctx.h"
 #include <map>
+#include <algorithm>
 #include <array>
 #include <cmath>
 
@@ -139,55 +140,60 @@ k_asm22(const int32_t* __restrict__ rp22, const int32_t* __restrict__ gptr,
     for (int i = threadIdx.x; i < 900; i += blockDim.x) sR[i] = c_R22[i];
     for (int i = threadIdx.x; i < 100; i += blockDim.x) sM[i] = c_M22[i];
     __syncthreads();
-    int64_t a = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (a >= n2) return;
-    int32_t e0 = rp22[a], d22 = rp22[a + 1] - e0;
-    int64_t base[3];
-    if (BLOCKS) {
+    // persistent CTAs: the reference tables are staged once per CTA, warps stride over the node rows
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t a = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; a < n2; a += nwarps) {
+        const int32_t e0 = rp22[a], d22 = rp22[a + 1] - e0;
+        int64_t base[3];
+        if (BLOCKS) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) base[k] = rowptr[k * n2 + a];
-    }
-    for (int j = lane; j < d22; j += 32) {
-        int32_t e = e0 + j;
-        double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        double mass = 0.0;
-        int32_t g1 = gptr[e + 1];
-        for (int32_t g = gptr[e]; g < g1; ++g) {
-            uint32_t id = glist[g];
-            uint32_t c = id / 100u;
-            int p = (int)(id - c * 100u);
-            double Ji[9], det;
-            load_geom(geom, c, Ji, det);
-            if (BLOCKS || STIFF) {
-                const double* R = sR + p * 9;
-                double T[9];
+            for (int k = 0; k < 3; ++k) base[k] = rowptr[k * n2 + a];
+        }
+        for (int j = lane; j < d22; j += 32) {
+            const int32_t e = e0 + j;
+            double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double mass = 0.0;
+            int32_t g = gptr[e];
+            const int32_t g1 = gptr[e + 1];
+            uint32_t id = g < g1 ? glist[g] : 0u;            // next contribution id is fetched one step ahead
+            for (; g < g1; ++g) {
+                const uint32_t idn = (g + 1 < g1) ? glist[g + 1] : 0u;
+                const uint32_t c = id / 100u;
+                const int p = (int)(id - c * 100u);
+                double Ji[9], det;
+                load_geom(geom, c, Ji, det);
+                if (BLOCKS || STIFF) {
+                    const double* R = sR + p * 9;
+                    double T[9];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int n = 0; n < 3; ++n)
+                            T[k * 3 + n] = R[k * 3] * Ji[n] + R[k * 3 + 1] * Ji[3 + n] + R[k * 3 + 2] * Ji[6 + n];
+#pragma unroll
+                    for (int m = 0; m < 3; ++m)
+#pragma unroll
+                        for (int n = 0; n < 3; ++n)
+                            G[m * 3 + n] += det * (Ji[m] * T[n] + Ji[3 + m] * T[3 + n] + Ji[6 + m] * T[6 + n]);
+                }
+                if (MASS) mass += det * sM[p];
+                id = idn;
+            }
+            const double tr = G[0] + G[4] + G[8];
+            if (BLOCKS) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
 #pragma unroll
-                    for (int n = 0; n < 3; ++n)
-                        T[k * 3 + n] = R[k * 3] * Ji[n] + R[k * 3 + 1] * Ji[3 + n] + R[k * 3 + 2] * Ji[6 + n];
-#pragma unroll
-                for (int m = 0; m < 3; ++m)
-#pragma unroll
-                    for (int n = 0; n < 3; ++n)
-                        G[m * 3 + n] += det * (Ji[m] * T[n] + Ji[3 + m] * T[3 + n] + Ji[6 + m] * T[6 + n]);
+                    for (int l = 0; l < 3; ++l) {
+                        double v = mu * G[l * 3 + k] + lmbda * G[k * 3 + l];
+                        if (k == l) v += mu * tr;
+                        vals[base[k] + (int64_t)l * d22 + j] = v;
+                    }
             }
-            if (MASS) mass += det * sM[p];
+            if (STIFF) k22[e] = tr;
+            if (MASS) m22[e] = mass;
         }
-        double tr = G[0] + G[4] + G[8];
-        if (BLOCKS) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    double v = mu * G[l * 3 + k] + lmbda * G[k * 3 + l];
-                    if (k == l) v += mu * tr;
-                    vals[base[k] + (int64_t)l * d22 + j] = v;
-                }
-        }
-        if (STIFF) k22[e] = tr;
-        if (MASS) m22[e] = mass;
     }
 }
 
@@ -333,6 +339,11 @@ void compute_geometry(mpet_ctx* ctx, cudaStream_t st) {
     LAUNCH_CHECK(ctx);
 }
 
+// persistent grid of k_asm22: 4 CTAs of 8 warps per SM (or fewer when there are fewer rows)
+static int asm22_grid(mpet_ctx* ctx, int64_t n2) {
+    return (int)std::min<int64_t>(grid_for(n2 * 32, 256), (int64_t)ctx->sm_count * 4);
+}
+
 static double* upload_small(mpet_ctx* ctx, const double* h, int n, cudaStream_t st, std::vector<void*>& tmp) {
     double* d = nullptr;
     CUDA_CHECK(cudaMalloc(&d, sizeof(double) * (n > 0 ? n : 1)));
@@ -354,11 +365,11 @@ void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
 
     const int threads = 256;
     if (ctx->k22) {
-        k_asm22<true, true, false><<<grid_for(n2 * 32, threads), threads, 0, st>>>(
+        k_asm22<true, true, false><<<asm22_grid(ctx, n2), threads, 0, st>>>(
             ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, n2, C.uu_mu, C.uu_lam,
             ctx->vals, ctx->k22, nullptr);
     } else {
-        k_asm22<true, false, false><<<grid_for(n2 * 32, threads), threads, 0, st>>>(
+        k_asm22<true, false, false><<<asm22_grid(ctx, n2), threads, 0, st>>>(
             ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, n2, C.uu_mu, C.uu_lam,
             ctx->vals, nullptr, nullptr);
     }
@@ -381,7 +392,7 @@ void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
 void ensure_m22(mpet_ctx* ctx, cudaStream_t st) {
     if (ctx->m22) return;
     ctx->m22 = dev_alloc<double>(ctx, ctx->g22.nnz);
-    k_asm22<false, false, true><<<grid_for(ctx->N2 * 32, 256), 256, 0, st>>>(
+    k_asm22<false, false, true><<<asm22_grid(ctx, ctx->N2), 256, 0, st>>>(
         ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, ctx->N2, 0, 0, nullptr,
         nullptr, ctx->m22);
     LAUNCH_CHECK(ctx);
@@ -392,7 +403,7 @@ void assemble_prec(mpet_ctx* ctx, cudaStream_t st) {
     const int A = ctx->A;
     if (!ctx->k22) {
         ctx->k22 = dev_alloc<double>(ctx, ctx->g22.nnz);
-        k_asm22<false, true, false><<<grid_for(ctx->N2 * 32, 256), 256, 0, st>>>(
+        k_asm22<false, true, false><<<asm22_grid(ctx, ctx->N2), 256, 0, st>>>(
             ctx->g22.rowptr, ctx->g22.gptr, ctx->g22.glist, ctx->geom, ctx->rowptr, ctx->N2, 0, 0, nullptr,
             ctx->k22, nullptr);
         LAUNCH_CHECK(ctx);

@@ -74,6 +74,11 @@ struct AmgHierarchy {
     int nrhs = 1;
     double* coarse_inv = nullptr;  // dense inverse on the coarsest level
     int64_t coarse_n = 0;
+    // polynomial mode (well-conditioned block): the whole "cycle" is poly_degree Chebyshev steps on [poly_lo, poly_hi]
+    int poly_degree = 0;
+    double* cyc_r = nullptr;       // work vectors of multi-cycle applications (development aid)
+    double* cyc_e = nullptr;
+    double poly_lo = 0.0, poly_hi = 0.0;
     int transition = -1;           // multi-GPU: index of the last distributed level (coarser ones are replicated)
     int64_t gather_count = 0;      // rows per rank in the padded replicated numbering
     double* gather_send = nullptr; // [gather_count * W] local slot of the all-gathered coarse right-hand side
@@ -163,7 +168,7 @@ struct mpet_ctx {
     struct KrylovWork* kw = nullptr;
     struct DistState* dist = nullptr;           // NCCL communicator + halo plan (dist.cu)
     AmgHierarchy* amg_u = nullptr;              // scalar P2 block, 3 right-hand sides
-    AmgHierarchy* amg_p[MPET_MAX_NETWORKS] = {};  // one per network
+    AmgHierarchy* amg_p[MPET_MAX_NETWORKS] = {};  // one per P1 field
     double* jac_dinv = nullptr;                 // Jacobi preconditioner (pc = 1)
     // the per-network V-cycles are independent of the displacement V-cycle: they run on their own streams
     cudaStream_t pc_stream[MPET_MAX_NETWORKS] = {};
@@ -232,7 +237,8 @@ bool staged_build_spmm_plan(mpet_ctx* ctx, const std::vector<int32_t>& rp, SpmmP
 void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr& M, const double* x, const double* b,
                  double* out, double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st);
 // dist.cu (multi-GPU)
-enum { DIST_PLAN_KRYLOV = 0, DIST_PLAN_P2W4 = 1, DIST_PLAN_P1W4 = 2, DIST_PLAN_P1W1 = 3, DIST_NPLANS = 4 };
+// P1WA: the A vertex fields of the merged pressure hierarchy (entry i*Nv + v)
+enum { DIST_PLAN_KRYLOV = 0, DIST_PLAN_P2W4 = 1, DIST_PLAN_P1W4 = 2, DIST_PLAN_P1W1 = 3, DIST_PLAN_P1WA = 4, DIST_NPLANS = 5 };
 bool dist_active(mpet_ctx* ctx);
 int dist_rank(mpet_ctx* ctx);
 int dist_nranks(mpet_ctx* ctx);

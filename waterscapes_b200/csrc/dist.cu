@@ -199,8 +199,13 @@ void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* sen
                         case DIST_PLAN_P2W4: for (int k = 0; k < 3; ++k) idx.push_back(4 * a + k); break;
                         case DIST_PLAN_P1W4: if (vertex) for (int k = 0; k < 3; ++k) idx.push_back(4 * a + k); break;
                         case DIST_PLAN_P1W1: if (vertex) idx.push_back(a); break;
+                        default: break;
                     }
                 }
+                if (pl == DIST_PLAN_P1WA)
+                    for (int i = 0; i < A; ++i)
+                        for (int64_t t = off[q]; t < off[q + 1]; ++t)
+                            if (nodes[t] < nv) idx.push_back((int32_t)((int64_t)i * nv + nodes[t]));
                 if (pl == DIST_PLAN_KRYLOV)
                     for (int i = 0; i < A; ++i)
                         for (int64_t t = off[q]; t < off[q + 1]; ++t)

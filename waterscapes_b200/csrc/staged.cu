@@ -631,7 +631,11 @@ static void spmm_pipe_lanes(mpet_ctx* ctx, const SpmmPlan& P, const DevCsr& M, c
     // P2 level (28 entries/row) 32 lanes 7.08 ms, 16: 5.06, 8: 4.33, 4: 3.33, 2: 3.41, 1: 3.70;
     // P1 and aggregated levels (<= 20 entries/row) 8 lanes 3.49 ms, 4: 3.23, 2: 3.15, 1: 3.03.
     // (development aid: MPET_SPM_LANES_HI / _LO override.)
+    // Longer rows (smoothed-aggregation levels, 50-200 entries) keep ~14-28 entries per lane.
     int lanes = mean > 20 ? env_cfg("MPET_SPM_LANES_HI", 64, 2) : env_cfg("MPET_SPM_LANES_LO", 64, 1);
+    if (mean > 160) lanes = 16;
+    else if (mean > 80) lanes = 8;
+    else if (mean > 40) lanes = 4;
     switch (lanes) {
         case 1: launch_spmm_pipe<W, 1, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
         case 2: launch_spmm_pipe<W, 2, EPI, CFG>(ctx, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
