@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the host logic of the multi-GPU path (cell partition + ghost layer,
+"""CPU, world_size 2 and 4 over gloo: the host logic of the multi-GPU path (cell partition + ghost layer,
 dof ownership, halo lists).  The numerical part is emulated with the oracle: a rank's local matrix
 times a consistent local vector must reproduce the global SpMV on owned rows, and one halo exchange
 driven by the send/recv lists must make the ghost entries right."""
@@ -44,8 +44,10 @@ def _worker(rank, world, port, n, results):
         from waterscapes_b200.mpet.dolfin_shim import FunctionSpace, UnitCubeMesh
         g = unit_cube_mesh(n)
         J = PARAMS["J"]
-        # cell partition: lower / upper half by cell index (cells are ordered layer by layer)
-        cell_owner = (np.arange(g.num_cells) >= g.num_cells // 2).astype(np.int64)
+        # cell partition into z-slabs by cell index (cells are ordered layer by layer, 6 n^2 per layer)
+        layer = np.arange(g.num_cells) // (6 * n * n)
+        bounds = [(n * r) // world for r in range(world + 1)]
+        cell_owner = np.searchsorted(np.asarray(bounds[1:]), layer, side="right").astype(np.int64)
         local = extract_local(g.coords, g.cells, cell_owner, rank)
         slab = box_slab((0, 0, 0), (1, 1, 1), n, n, n, rank, world)
         assert np.array_equal(slab.global_vertex[slab.cells], local.global_vertex[local.cells])
@@ -101,10 +103,10 @@ def _worker(rank, world, port, n, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [6])
-def test_partition_and_halo_lists_world2(n):
+@pytest.mark.parametrize("world,n", [(2, 6), (4, 12)])
+def test_partition_and_halo_lists(world, n):
     port = _free_port()
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(2, port, n, results), nprocs=2, join=True)
-    assert results.get(0) and results.get(1)
+    mp.spawn(_worker, args=(world, port, n, results), nprocs=world, join=True)
+    assert all(results.get(r) for r in range(world))

@@ -526,6 +526,9 @@ const int kLanczosSteps = 40;
 // 3 cycles: 350 / 1989; 2 cycles, degree 4: 341 / 1942; 4 cycles: 340 / 1995 (plateau = exact block solves).
 const int kP1Cycles = 2;
 const int kP1Degree = 4;
+// multi-GPU: the transition to the replicated levels uses plain aggregation (weaker coarse correction); measured
+// at N = 2 (91^3): 2 cycles 541-600 iterations / 4417 ms, 3 cycles 473 / 3981, 4 cycles 462 / 4241
+const int kP1CyclesDist = 3;
 const double kChebRatio = 4.0;    // smooth the upper [lambda_max / ratio, lambda_max] of D^-1 A
 const int64_t kCoarseMax = 300;
 const int kMaxLevels = 12;
@@ -1161,9 +1164,10 @@ static void cycles(mpet_ctx* ctx, AmgHierarchy& H, int ncycles, const double* b,
 void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
     static const bool want_streams = []() { const char* e = getenv("MPET_PC_STREAMS"); return !(e && e[0] == '0'); }();
-    static const int p_cycles = []() { const char* e = getenv("MPET_P_CYCLES"); return e ? std::max(1, atoi(e)) : kP1Cycles; }();
+    static const int p_cycles = []() { const char* e = getenv("MPET_P_CYCLES"); return e ? std::max(1, atoi(e)) : 0; }();
     static const int u_cycles = []() { const char* e = getenv("MPET_U_CYCLES"); return e ? std::max(1, atoi(e)) : 1; }();
     const bool fork = want_streams && ctx->A > 0 && !dist_active(ctx);
+    const int p_cyc = p_cycles > 0 ? p_cycles : (dist_active(ctx) ? kP1CyclesDist : kP1Cycles);
     if (fork) {
         if (ctx->pc_streams_ready < ctx->A) {
             int lo = 0, hi = 0;
@@ -1180,18 +1184,44 @@ void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaS
             const int64_t off = 4 * n2 + (int64_t)i * nv;
             AmgHierarchy& H = *ctx->amg_p[i];
             CUDA_CHECK(cudaStreamWaitEvent(ctx->pc_stream[i], ctx->pc_fork, 0));
-            cycles<1>(ctx, H, H.poly_degree ? 1 : p_cycles, r + off, z + off, done, ctx->pc_stream[i]);
+            cycles<1>(ctx, H, H.poly_degree ? 1 : p_cyc, r + off, z + off, done, ctx->pc_stream[i]);
             CUDA_CHECK(cudaEventRecord(ctx->pc_join[i], ctx->pc_stream[i]));
         }
         cycles<4>(ctx, *ctx->amg_u, u_cycles, r, z, done, st);
         for (int i = 0; i < ctx->A; ++i) CUDA_CHECK(cudaStreamWaitEvent(st, ctx->pc_join[i], 0));
         return;
     }
+    if (want_streams && ctx->A > 0 && dist_has_lane1(ctx)) {
+        // multi-GPU: all P1-field cycles on ONE side stream with their own communicator (lane 1); their many small
+        // halo exchanges then overlap the displacement cycle instead of queueing behind it
+        if (ctx->pc_streams_ready < 1) {
+            int lo = 0, hi = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            if (!ctx->pc_fork) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->pc_fork, cudaEventDisableTiming));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->pc_stream[0], cudaStreamNonBlocking, hi));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ctx->pc_join[0], cudaEventDisableTiming));
+            ctx->pc_streams_ready = 1;
+        }
+        cudaStream_t sp = ctx->pc_stream[0];
+        CUDA_CHECK(cudaEventRecord(ctx->pc_fork, st));
+        CUDA_CHECK(cudaStreamWaitEvent(sp, ctx->pc_fork, 0));
+        ctx->dist_lane = 1;
+        for (int i = 0; i < ctx->A; ++i) {
+            const int64_t off = 4 * n2 + (int64_t)i * nv;
+            AmgHierarchy& H = *ctx->amg_p[i];
+            cycles<1>(ctx, H, H.poly_degree ? 1 : p_cyc, r + off, z + off, done, sp);
+        }
+        ctx->dist_lane = 0;
+        CUDA_CHECK(cudaEventRecord(ctx->pc_join[0], sp));
+        cycles<4>(ctx, *ctx->amg_u, u_cycles, r, z, done, st);
+        CUDA_CHECK(cudaStreamWaitEvent(st, ctx->pc_join[0], 0));
+        return;
+    }
     cycles<4>(ctx, *ctx->amg_u, u_cycles, r, z, done, st);
     for (int i = 0; i < ctx->A; ++i) {
         const int64_t off = 4 * n2 + (int64_t)i * nv;
         AmgHierarchy& H = *ctx->amg_p[i];
-        cycles<1>(ctx, H, H.poly_degree ? 1 : p_cycles, r + off, z + off, done, st);
+        cycles<1>(ctx, H, H.poly_degree ? 1 : p_cyc, r + off, z + off, done, st);
     }
 }
 

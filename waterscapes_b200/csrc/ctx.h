@@ -174,6 +174,7 @@ struct mpet_ctx {
     cudaStream_t pc_stream[MPET_MAX_NETWORKS] = {};
     cudaEvent_t pc_fork = nullptr, pc_join[MPET_MAX_NETWORKS] = {};
     int pc_streams_ready = 0;
+    int dist_lane = 0;           // which NCCL communicator / staging buffers dist_halo and dist_allgather use (dist.cu)
 };
 
 // ---- helpers --------------------------------------------------------------------------------
@@ -240,6 +241,7 @@ void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr&
 // P1WA: the A vertex fields of the merged pressure hierarchy (entry i*Nv + v)
 enum { DIST_PLAN_KRYLOV = 0, DIST_PLAN_P2W4 = 1, DIST_PLAN_P1W4 = 2, DIST_PLAN_P1W1 = 3, DIST_PLAN_P1WA = 4, DIST_NPLANS = 5 };
 bool dist_active(mpet_ctx* ctx);
+bool dist_has_lane1(mpet_ctx* ctx);
 int dist_rank(mpet_ctx* ctx);
 int dist_nranks(mpet_ctx* ctx);
 const uint8_t* dist_owned_mask(mpet_ctx* ctx);

@@ -34,6 +34,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;     // optional (NCCL >= 2.18)
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
 
@@ -60,6 +61,7 @@ void load_nccl() {
     RESOLVE(Broadcast, "ncclBroadcast")
     RESOLVE(GetErrorString, "ncclGetErrorString")
 #undef RESOLVE
+    *(void**)(&g_nccl.CommSplit) = dlsym(g_nccl.handle, "ncclCommSplit");
 }
 
 #define NCCL_CHECK(call)                                                                     \
@@ -130,6 +132,11 @@ struct HaloPlan {
 
 struct DistState {
     ncclComm_t comm = nullptr;
+    // second communicator + staging buffers ("lane 1"): the P1-field cycles of the preconditioner exchange their
+    // halos on their own stream while the displacement cycle runs on the main one (both are latency-bound)
+    ncclComm_t comm2 = nullptr;
+    double* send_buf2 = nullptr;
+    double* recv_buf2 = nullptr;
     int rank = 0, nranks = 1;
     std::vector<int> nbr;                 // neighbour ranks (ascending)
     HaloPlan plan[DIST_NPLANS];           // Krylov vectors, P2 x W4, P1 x W4, P1 x W1 level vectors
@@ -156,11 +163,15 @@ void dist_attach(mpet_ctx* ctx, const void* uid, int rank, int nranks) {
     memcpy(&id, uid, 128);
     CUDA_CHECK(cudaSetDevice(ctx->device));
     NCCL_CHECK(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
+    if (g_nccl.CommSplit && !getenv("MPET_NO_LANE1")) {
+        if (g_nccl.CommSplit(d->comm, 0, rank, &d->comm2, nullptr) != 0) d->comm2 = nullptr;
+    }
     ctx->dist = d;
 }
 
 void dist_free(mpet_ctx* ctx) {
     if (!ctx->dist) return;
+    if (ctx->dist->comm2) g_nccl.CommDestroy(ctx->dist->comm2);
     if (ctx->dist->comm) g_nccl.CommDestroy(ctx->dist->comm);
     delete ctx->dist;
     ctx->dist = nullptr;
@@ -221,6 +232,10 @@ void dist_set_halo(mpet_ctx* ctx, int nnbr, const int* ranks, const int64_t* sen
     }
     d->send_buf = dev_alloc<double>(ctx, maxlen);
     d->recv_buf = dev_alloc<double>(ctx, maxlen);
+    if (d->comm2) {
+        d->send_buf2 = dev_alloc<double>(ctx, maxlen);
+        d->recv_buf2 = dev_alloc<double>(ctx, maxlen);
+    }
     // ownership mask of the Krylov vectors (solver-internal layout; pad lanes stay 0)
     std::vector<uint8_t> own(ctx->Nint, 0);
     for (int64_t a = 0; a < n2; ++a)
@@ -247,21 +262,25 @@ void dist_halo(mpet_ctx* ctx, int plan, double* v, bool reverse, const int* done
     const std::vector<int64_t>& poff = reverse ? P.recv_off : P.send_off;
     const std::vector<int64_t>& uoff = reverse ? P.send_off : P.recv_off;
     const int64_t np = poff[nn], nu = uoff[nn];
-    if (np) { k_pack<<<grid_for(np, 256), 256, 0, st>>>(pack_idx, np, v, d->send_buf, done); LAUNCH_CHECK(ctx); }
+    const bool lane1 = ctx->dist_lane == 1 && d->comm2 != nullptr;
+    ncclComm_t comm = lane1 ? d->comm2 : d->comm;
+    double* sbuf = lane1 ? d->send_buf2 : d->send_buf;
+    double* rbuf = lane1 ? d->recv_buf2 : d->recv_buf;
+    if (np) { k_pack<<<grid_for(np, 256), 256, 0, st>>>(pack_idx, np, v, sbuf, done); LAUNCH_CHECK(ctx); }
     NCCL_CHECK(g_nccl.GroupStart());
     for (int q = 0; q < nn; ++q) {
         const int64_t cs = poff[q + 1] - poff[q], cr = uoff[q + 1] - uoff[q];
-        if (cs) NCCL_CHECK(g_nccl.Send(d->send_buf + poff[q], (size_t)cs, NCCL_FLOAT64, d->nbr[q], d->comm, st));
-        if (cr) NCCL_CHECK(g_nccl.Recv(d->recv_buf + uoff[q], (size_t)cr, NCCL_FLOAT64, d->nbr[q], d->comm, st));
+        if (cs) NCCL_CHECK(g_nccl.Send(sbuf + poff[q], (size_t)cs, NCCL_FLOAT64, d->nbr[q], comm, st));
+        if (cr) NCCL_CHECK(g_nccl.Recv(rbuf + uoff[q], (size_t)cr, NCCL_FLOAT64, d->nbr[q], comm, st));
     }
     NCCL_CHECK(g_nccl.GroupEnd());
     if (reverse) {
         for (int q = 0; q < nn; ++q) {      // rank order: deterministic sums
             const int64_t cr = uoff[q + 1] - uoff[q];
-            if (cr) { k_unpack<<<grid_for(cr, 256), 256, 0, st>>>(unpack_idx + uoff[q], cr, d->recv_buf + uoff[q], v, 1, done); LAUNCH_CHECK(ctx); }
+            if (cr) { k_unpack<<<grid_for(cr, 256), 256, 0, st>>>(unpack_idx + uoff[q], cr, rbuf + uoff[q], v, 1, done); LAUNCH_CHECK(ctx); }
         }
     } else if (nu) {
-        k_unpack<<<grid_for(nu, 256), 256, 0, st>>>(unpack_idx, nu, d->recv_buf, v, 0, done);
+        k_unpack<<<grid_for(nu, 256), 256, 0, st>>>(unpack_idx, nu, rbuf, v, 0, done);
         LAUNCH_CHECK(ctx);
     }
 }
@@ -272,8 +291,11 @@ const std::vector<uint8_t>& dist_own_nodes(mpet_ctx* ctx) { return ctx->dist->ow
 
 // equal-count all-gather of doubles (device buffers)
 void dist_allgather(mpet_ctx* ctx, const double* send, double* recv, int64_t count, cudaStream_t st) {
-    NCCL_CHECK(g_nccl.AllGather(send, recv, (size_t)count, NCCL_FLOAT64, ctx->dist->comm, st));
+    DistState* d = ctx->dist;
+    ncclComm_t comm = (ctx->dist_lane == 1 && d->comm2) ? d->comm2 : d->comm;
+    NCCL_CHECK(g_nccl.AllGather(send, recv, (size_t)count, NCCL_FLOAT64, comm, st));
 }
+bool dist_has_lane1(mpet_ctx* ctx) { return dist_active(ctx) && ctx->dist->comm2 != nullptr; }
 // broadcast of raw bytes (device buffer) from `root`
 void dist_bcast_bytes(mpet_ctx* ctx, void* buf, int64_t nbytes, int root, cudaStream_t st) {
     NCCL_CHECK(g_nccl.Broadcast(buf, buf, (size_t)nbytes, NCCL_INT8, root, ctx->dist->comm, st));
