@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 METRIC = "mpet_timestep_dof_per_s"
 UNIT = "DOF/s"
 DEFAULT_CONFIG = "cfg5"          # A=3, n=72 per GPU: ~10.3 M dofs per GPU (BASELINE.json configs[4])
-CPU_SAMPLE_N = 10                # bounded CPU sample of the same workload family
+CPU_SAMPLE_N = 18                # bounded CPU sample of the same workload family (~175 k dofs, ~10-20 s of CPU work)
 
 
 def parse_args():
@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--maxit", type=int, default=10000)
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--formulation", default="standard", choices=["standard", "total-pressure"],
+                    help="standard = MPETSolver (the headline); total-pressure = MPETTotalPressureSolver on the same "
+                         "workload (SURVEY.md 8f.1), reported as extra information")
     return ap.parse_args()
 
 
@@ -244,7 +247,7 @@ def main():
     import torch
     import torch.distributed as dist
     from waterscapes_b200.workloads import make_problem, CONFIGS
-    from waterscapes_b200.mpet import MPETSolver
+    from waterscapes_b200.mpet import MPETSolver, MPETTotalPressureSolver
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
@@ -273,10 +276,16 @@ def main():
     else:
         problem, sp, init = make_problem(args.config, n)
     sp = dict(sp, direct_solver=False, krylov_rtol=args.rtol, krylov_maxit=args.maxit)
-    solver = MPETSolver(problem, sp, device=local_rank, partition=partition)
+    tp = args.formulation == "total-pressure"
+    solver = (MPETTotalPressureSolver if tp else MPETSolver)(problem, sp, device=local_rank, partition=partition)
     eng = solver.engine
     S = eng.sizes
-    init(solver)
+    if tp:      # initial network pressures = boundary data, total pressure 0 (the workload's own init targets MPETSolver)
+        problem.time.assign(0.0)
+        for i in range(int(problem.params["J"])):
+            solver.up_.set_sub(solver._net_sub(i), problem.p_bar[i])
+    else:
+        init(solver)
     dt = sp["dt"]
 
     def one_step():
@@ -358,12 +367,15 @@ def main():
                 "avg_launch_ms": spmv_ms, "launches_timed": prof["spmv"]["count"],
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                 "share_of_step": {"spmv": prof["spmv"]["ms"] / ms, "preconditioner": prof["pc"]["ms"] / ms,
-                                  "assemble_lhs": prof["assemble"]["ms"] / ms, "rhs_prev": prof["rhs"]["ms"] / ms}}
+                                  "assemble_lhs": prof["assemble"]["ms"] / ms, "rhs_prev": prof["rhs"]["ms"] / ms,
+                                  "halo_and_collectives_main_stream": prof["comm"]["ms"] / ms},
+                "comm_ops_timed": prof["comm"]["count"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: [P2]^3x[P1]^%d MPET on BoxMesh(%d^3) per GPU, %d cells, %d dofs, %d nnz; "
+            "config": {"formulation": args.formulation,
+                       "workload": "%s: [P2]^3x[P1]^%d MPET on BoxMesh(%d^3) per GPU, %d cells, %d dofs, %d nnz; "
                                    "step = assemble A + b, Dirichlet, MINRES+block-AMG to rtol %g"
                                    % (args.config, S["A"], n, S["Nc"], N, S["nnz"], args.rtol),
                        "dofs_per_gpu": N, "nnz_per_gpu": S["nnz"], "rtol": args.rtol, "krylov_iterations": iters,

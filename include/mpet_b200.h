@@ -159,7 +159,8 @@ int mpet_set_halo(mpet_ctx* ctx, int n_neighbours, const int* ranks_host, const 
 int64_t mpet_launch_count(mpet_ctx* ctx, int reset);
 /* CUDA-event profile of the library's own launches (bench.py's live roofline measurement).
  * enable: 1/0 = reset counters and switch on/off, -1 = leave unchanged.  out_host (nullable) f64[16]:
- * [0..7] device ms per category (0 SpMV of A, 1 preconditioner, 3 assemble_lhs, 4 rhs_prev),
+ * [0..7] device ms per category (0 SpMV of A, 1 preconditioner, 3 assemble_lhs, 4 rhs_prev,
+ * 5 halo exchanges + collectives on the main stream; categories 1 and 5 overlap),
  * [8..15] launch-group counts.  Synchronises the device. */
 int mpet_profile(mpet_ctx* ctx, int enable, double* out_host);
 int64_t mpet_device_bytes(mpet_ctx* ctx);

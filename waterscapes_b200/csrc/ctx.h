@@ -85,7 +85,7 @@ struct AmgHierarchy {
 };
 
 // CUDA-event profiler: per-category device time of the launches made inside the library
-enum { PROF_SPMV = 0, PROF_PC = 1, PROF_VEC = 2, PROF_ASM = 3, PROF_RHS = 4, PROF_NCAT = 8 };
+enum { PROF_SPMV = 0, PROF_PC = 1, PROF_VEC = 2, PROF_ASM = 3, PROF_RHS = 4, PROF_COMM = 5, PROF_NCAT = 8 };
 struct Prof {
     bool on = false;
     struct Span { int cat; cudaEvent_t a, b; };

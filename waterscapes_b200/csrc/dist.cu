@@ -263,6 +263,7 @@ void dist_halo(mpet_ctx* ctx, int plan, double* v, bool reverse, const int* done
     const std::vector<int64_t>& uoff = reverse ? P.send_off : P.recv_off;
     const int64_t np = poff[nn], nu = uoff[nn];
     const bool lane1 = ctx->dist_lane == 1 && d->comm2 != nullptr;
+    cudaEvent_t pe = lane1 ? nullptr : prof_begin(ctx, st);      // main-stream exchanges are on the critical path
     ncclComm_t comm = lane1 ? d->comm2 : d->comm;
     double* sbuf = lane1 ? d->send_buf2 : d->send_buf;
     double* rbuf = lane1 ? d->recv_buf2 : d->recv_buf;
@@ -283,6 +284,7 @@ void dist_halo(mpet_ctx* ctx, int plan, double* v, bool reverse, const int* done
         k_unpack<<<grid_for(nu, 256), 256, 0, st>>>(unpack_idx, nu, rbuf, v, 0, done);
         LAUNCH_CHECK(ctx);
     }
+    prof_end(ctx, PROF_COMM, pe, st);
 }
 
 int dist_rank(mpet_ctx* ctx) { return ctx->dist ? ctx->dist->rank : 0; }
@@ -292,8 +294,10 @@ const std::vector<uint8_t>& dist_own_nodes(mpet_ctx* ctx) { return ctx->dist->ow
 // equal-count all-gather of doubles (device buffers)
 void dist_allgather(mpet_ctx* ctx, const double* send, double* recv, int64_t count, cudaStream_t st) {
     DistState* d = ctx->dist;
-    ncclComm_t comm = (ctx->dist_lane == 1 && d->comm2) ? d->comm2 : d->comm;
-    NCCL_CHECK(g_nccl.AllGather(send, recv, (size_t)count, NCCL_FLOAT64, comm, st));
+    const bool lane1 = ctx->dist_lane == 1 && d->comm2;
+    cudaEvent_t pe = lane1 ? nullptr : prof_begin(ctx, st);
+    NCCL_CHECK(g_nccl.AllGather(send, recv, (size_t)count, NCCL_FLOAT64, lane1 ? d->comm2 : d->comm, st));
+    prof_end(ctx, PROF_COMM, pe, st);
 }
 bool dist_has_lane1(mpet_ctx* ctx) { return dist_active(ctx) && ctx->dist->comm2 != nullptr; }
 // broadcast of raw bytes (device buffer) from `root`
@@ -307,5 +311,7 @@ void dist_allreduce_max(mpet_ctx* ctx, double* dev_scalars, int count, cudaStrea
 
 void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st) {
     if (!dist_active(ctx)) return;
+    cudaEvent_t pe = prof_begin(ctx, st);
     NCCL_CHECK(g_nccl.AllReduce(dev_scalars, dev_scalars, (size_t)count, NCCL_FLOAT64, NCCL_SUM, ctx->dist->comm, st));
+    prof_end(ctx, PROF_COMM, pe, st);
 }

@@ -448,10 +448,12 @@ constexpr int kBlkCapV[kNumBlkCfg] = {BlkCfg0::kCapV, BlkCfg1::kCapV, BlkCfg2::k
 
 using SpmCfg0 = SpmCfg<384, 4, 2048, 256, 2>;    // 768 threads per SM: 85 registers, no spills in the W = 4 Chebyshev step
 using SpmCfg1 = SpmCfg<512, 4, 2048, 256, 2>;
-using SpmCfg2 = SpmCfg<384, 3, 1024, 128, 2>;    // small ring: most of the 228 KB stays L1 (no gain measured)
-constexpr int kNumSpmCfg = 3;
-constexpr int kSpmCap[kNumSpmCfg] = {2048, 2048, 1024};
-constexpr int kSpmRows[kNumSpmCfg] = {256, 256, 128};
+using SpmCfg2 = SpmCfg<384, 3, 1024, 128, 2>;    // small ring: most of the 228 KB stays L1
+using SpmCfg3 = SpmCfg<256, 3, 1024, 128, 4>;
+using SpmCfg4 = SpmCfg<512, 3, 1024, 128, 2>;
+constexpr int kNumSpmCfg = 5;
+constexpr int kSpmCap[kNumSpmCfg] = {2048, 2048, 1024, 1024, 1024};
+constexpr int kSpmRows[kNumSpmCfg] = {256, 256, 128, 128, 128};
 
 int env_cfg(const char* name, int n, int dflt) {
     const char* e = getenv(name);
@@ -666,6 +668,8 @@ void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr&
     switch (P.cfg) {
         case 1: spmm_pipe_cfg<SpmCfg1>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
         case 2: spmm_pipe_cfg<SpmCfg2>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 3: spmm_pipe_cfg<SpmCfg3>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
+        case 4: spmm_pipe_cfg<SpmCfg4>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
         default: spmm_pipe_cfg<SpmCfg0>(ctx, W, epi, P, M, x, b, out, d, dinv, c1, c2, done, st); break;
     }
 }

@@ -195,7 +195,7 @@ class Engine:
         """Read (and optionally reset/switch) the library's CUDA-event profile."""
         out = (C.c_double * 16)()
         self._ck(self.lib.mpet_profile(self._ctx, int(enable), out))
-        names = ["spmv", "pc", "vec", "assemble", "rhs"]
+        names = ["spmv", "pc", "vec", "assemble", "rhs", "comm"]
         return {n: dict(ms=float(out[i]), count=int(out[8 + i])) for i, n in enumerate(names)}
 
     def device_bytes(self):
