@@ -262,6 +262,15 @@ __global__ void k_lz_next(int64_t n, const double* __restrict__ w, double inv_be
     v[i] = w[i] * inv_beta;
 }
 
+__global__ void k_expand4(int64_t n, const double* __restrict__ in, double* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < 4 * n) out[i] = in[i >> 2];
+}
+__global__ void k_take4(int64_t n, const double* __restrict__ in, double* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[4 * i];
+}
+
 __global__ void k_add_inplace(int64_t n, const double* __restrict__ e, double* __restrict__ x, const int* __restrict__ done) {
     if (done && *done) return;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -606,6 +615,12 @@ void launch_plain(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const do
 }
 
 // Chebyshev smoothing on level L: x_out = S(b, x_in); x_in == nullptr means zero initial guess.
+// development aid: MPET_ALL_HALOS=1 restores the exchange after every level operation
+static bool skip_redundant_halos() {
+    static const bool v = []() { const char* e = getenv("MPET_ALL_HALOS"); return !(e && e[0] == '1'); }();
+    return v;
+}
+
 static int g_p_degree() {
     static const int d = []() { const char* e = getenv("MPET_P_DEGREE"); return e ? std::max(1, atoi(e)) : kP1Degree; }();
     return d;
@@ -641,8 +656,11 @@ void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, 
         }
         if (bounce)
             CUDA_CHECK(cudaMemcpyAsync(x_out, dst, sizeof(double) * n * W, cudaMemcpyDeviceToDevice, st));
-        // distributed level: owned rows are right, ghost rows are refreshed from their owners
-        if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, bounce ? x_out : dst, false, done, st);
+        // distributed level: owned rows are right, ghost rows are refreshed from their owners.  The first step
+        // from a zero guess is diagonal (x = c * dinv * b): its ghost rows are already right because b's ghosts
+        // are valid and dinv's ghosts were taken from their owners at set-up (sync_ghost_diagonal)
+        const bool diagonal_step = (k == 0 && x_in == nullptr && skip_redundant_halos());
+        if (L.halo_plan >= 0 && !diagonal_step) dist_halo(ctx, L.halo_plan, bounce ? x_out : dst, false, done, st);
         cur = dst;
     }
 }
@@ -680,7 +698,9 @@ void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x,
     double* xc = C.x + (int64_t)W * nc;   // second half of the coarse x buffer holds the coarse solution
     vcycle<W>(ctx, H, lev + 1, C.b, xc, done, st);
     launch_plain<W>(ctx, C.P, C.planP, xc, x, 1.0, done, st);                                  // prolong + correct
-    if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, x, false, done, st);
+    // the prolongators carry the rows of the ghost nodes too and the coarse solution is valid on ghosts / replicated:
+    // x stays consistent without an exchange
+    if (L.halo_plan >= 0 && !skip_redundant_halos()) dist_halo(ctx, L.halo_plan, x, false, done, st);
     chebyshev<W>(ctx, L, b, x, x, done, st);                                                   // post-smooth
 }
 
@@ -971,7 +991,7 @@ HostCsr distributed_transition(mpet_ctx* ctx, AmgHierarchy& H, int W, cudaStream
     P.nrows = n; P.ncols = Ac.nrows;
     P.rp.assign(n + 1, 0);
     for (int64_t i = 0; i < n; ++i) {
-        if (ownn[i] && g[i] >= 0) { P.ci.push_back((int32_t)g[i]); P.v.push_back(1.0); }
+        if (g[i] >= 0) { P.ci.push_back((int32_t)g[i]); P.v.push_back(1.0); }      // ghost rows too: no exchange after it
         P.rp[i + 1] = (int32_t)P.ci.size();
     }
     R.nrows = maxcount; R.ncols = n;
@@ -1059,6 +1079,26 @@ DevCsr masked_block(mpet_ctx* ctx, const NodeGraph& g, const double* vals, doubl
     return M;
 }
 
+// multi-GPU: the local matrix misses part of the ghost rows, so their diagonal is wrong; take it from the owners
+// (scalar_plan: DIST_PLAN_P1W1 for vertex levels, -1 for the scalar P2 level, which goes through a 4-wide copy)
+void sync_ghost_diagonal(mpet_ctx* ctx, AmgLevel& L, bool p2_level, cudaStream_t st) {
+    if (!dist_active(ctx)) return;
+    const int64_t n = L.A.nrows;
+    if (!p2_level) {
+        dist_halo(ctx, DIST_PLAN_P1W1, L.dinv, false, nullptr, st);
+    } else {
+        double* tmp = nullptr;
+        CUDA_CHECK(cudaMalloc(&tmp, sizeof(double) * 4 * n));
+        k_expand4<<<grid_for(4 * n, 256), 256, 0, st>>>(n, L.dinv, tmp);
+        LAUNCH_CHECK(ctx);
+        dist_halo(ctx, DIST_PLAN_P2W4, tmp, false, nullptr, st);
+        k_take4<<<grid_for(n, 256), 256, 0, st>>>(n, tmp, L.dinv);
+        LAUNCH_CHECK(ctx);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+}
+
 // P2 -> P1 embedding (rows: P2 nodes, cols: vertices); Dirichlet rows/cols dropped
 HostCsr p2_to_p1(int64_t nv, int64_t ne, const std::vector<int32_t>& edge_v, const std::vector<uint8_t>& mask2) {
     HostCsr P;
@@ -1121,11 +1161,13 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         AmgLevel L0;
         L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->coef.p_mu, ctx->bc_mask, &L0.dinv, st);
         if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P2W4;
+        sync_ghost_diagonal(ctx, L0, true, st);
         H->levels.push_back(L0);
         AmgLevel L1;
         L1.A = masked_block(ctx, ctx->g11, ctx->l11, ctx->coef.p_mu, ctx->bc_mask /* vertices are the first Nv nodes */,
                             &L1.dinv, st);
         if (dist_active(ctx)) L1.halo_plan = DIST_PLAN_P1W4;
+        sync_ghost_diagonal(ctx, L1, false, st);
         HostCsr P = p2_to_p1(nv, ctx->Ne, edge_v, mask2);
         L1.P = upload(ctx, P);
         L1.R = upload(ctx, transpose(P));
@@ -1150,6 +1192,7 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         L0.A = masked_block(ctx, ctx->g11, ctx->pp11 + (int64_t)i * ctx->g11.nnz, 1.0,
                             ctx->bc_mask + 3 * n2 + (int64_t)i * nv, &L0.dinv, st);
         if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P1W1;
+        sync_ghost_diagonal(ctx, L0, false, st);
         H->levels.push_back(L0);
         // spectrum of D^-1 A: a small condition number (mass-dominated field) is inverted far more accurately --
         // and cheaper -- by a Chebyshev polynomial on the whole spectrum than by a V-cycle, and MINRES on this
