@@ -51,3 +51,51 @@ def test_iterative_time_loop_tracks_direct():
     assert len(out) == len(ref) == 2
     assert np.linalg.norm(out[-1] - ref[-1]) / np.linalg.norm(ref[-1]) < 1e-8
     assert all(m["converged"] for m in mon)
+
+
+def test_lanczos_bounds_and_polynomial_mode():
+    """The spectral bounds that select the polynomial mode (oracle/krylov.py, mirrored by amg.cu) against
+    scipy's eigensolver, and the accuracy of the resulting Chebyshev inverse."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle.krylov import lanczos_bounds, poly_degree, ScalarAMG, POLY_TARGET
+    o = _problem(5)
+    o.K = [1e-4, 1e-4]                       # mass-dominated network blocks (cond(D^-1 A) ~ 5)
+    M = o.assemble_prec().tocsr()
+    d = o.space.p_dofs(0)
+    A = M[d][:, d].tocsr()
+    dinv = 1.0 / A.diagonal()
+    lmin, lmax = lanczos_bounds(A, dinv)
+    Dm = sp.diags(np.sqrt(dinv))
+    ev = np.linalg.eigvalsh((Dm @ A @ Dm).toarray())
+    # Ritz values converge from inside the spectrum; the bounds are padded by 3 % / 2 % where they are used
+    assert 0 <= lmin - ev[0] < 1e-3 * ev[0] and 0 <= ev[-1] - lmax < 1e-3 * ev[-1]
+    h = ScalarAMG(A, allow_polynomial=True, cycles=2, degree=4)
+    assert h.poly is not None and h.poly[2] == poly_degree(h.poly[0], h.poly[1])
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(A.shape[0])
+    x = h.apply(b)[:, 0]
+    xe = spla.spsolve(A.tocsc(), b)
+    # error in the A-norm relative to the solution: below the residual-polynomial target (with slack)
+    e = x - xe
+    assert np.sqrt(e @ (A @ e)) < 5 * POLY_TARGET * np.sqrt(xe @ (A @ xe))
+    # the polynomial preconditioner is symmetric positive definite
+    c = rng.standard_normal(A.shape[0])
+    assert abs(h.apply(b)[:, 0] @ c - b @ h.apply(c)[:, 0]) < 1e-10 * abs(b @ h.apply(c)[:, 0]) + 1e-12
+    assert b @ x > 0
+
+
+def test_drop_small_preserves_row_sums_and_symmetry():
+    import scipy.sparse as sp
+    from oracle.krylov import drop_small
+    rng = np.random.default_rng(1)
+    n = 200
+    B = sp.random(n, n, density=0.05, random_state=3, format="csr")
+    B.data[np.abs(B.data) < 0.5] *= 0.01          # many tiny entries
+    S = (B + B.T).tocsr()
+    A = (S + sp.diags(np.asarray(abs(S).sum(axis=1)).ravel() + 1.0)).tocsr()   # strictly diagonally dominant: SPD
+    D = drop_small(A, 0.01)
+    assert D.nnz < A.nnz
+    assert np.allclose(np.asarray(D.sum(axis=1)).ravel(), np.asarray(A.sum(axis=1)).ravel())
+    assert abs(D - D.T).max() < 1e-14
+    assert np.all(np.linalg.eigvalsh(D.toarray()) > 0)
