@@ -144,7 +144,7 @@ int mpet_pc_apply(mpet_ctx* ctx, const double* r_dev, double* z_dev, void* strea
  *                         receives from q, as two concatenated device arrays with host offsets
  *                         [n_neighbours+1]; both sides list a shared node in the same order.
  *                         owned_nodes_dev u8[N2]: 1 where this rank owns the node (hence all its dofs).
- * After that mpet_solve (MINRES) refreshes ghost entries after every SpMV, counts each dof once in the
+ * After that mpet_solve (MINRES or GMRES) refreshes ghost entries after every SpMV, counts each dof once in the
  * dot products and all-reduces them.  The AMG V-cycles run distributed on the mesh-defined levels (P2, P1:
  * halo exchange after every smoothing step) and replicated below (restricted residual all-gathered), so the
  * preconditioner is the same operator for any number of GPUs. */

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, results):
+def _worker(rank, world, port, n, results, nonsym=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -28,16 +28,26 @@ def _worker(rank, world, port, n, results):
         from waterscapes_b200.parallel import box_slab, Partition, node_global_keys
         from waterscapes_b200.workloads import make_problem
         from waterscapes_b200.mpet import MPETSolver, BoxMesh
-        box = ((0.0, 0.0, 0.0), (120.0, 120.0, 240.0))
+        cfg = "cfg1" if nonsym else "cfg5"
+        box = ((0.0, 0.0, 0.0), (1.0, 1.0, 2.0)) if nonsym else ((0.0, 0.0, 0.0), (120.0, 120.0, 240.0))
         nz = 2 * n
         steps = 2
+
+        def tune(problem, sp):
+            if nonsym:
+                # non-symmetric exchange (the reference's own MMS test, test_convergence_mpetsolver.py:116):
+                # MPETSolver picks GMRES; direct_solver=True = the rtol 1e-12, restart 100 preset
+                problem.params["S"] = ((0.0, 2.0), (1.0, 0.0))
+                return dict(sp, direct_solver=True, T=steps * sp["dt"])
+            # nu = 0.49 instead of cfg5's 0.4999: two Krylov solutions of the nearly incompressible system agree
+            # only to ~cond * rtol (1.5e-8 observed at rtol 1e-11), which would test MINRES, not the partition
+            problem.params["nu"] = 0.49
+            return dict(sp, direct_solver=False, krylov_rtol=1e-11, T=steps * sp["dt"])
+
         # distributed run
         local = box_slab(box[0], box[1], n, n, nz, rank, world)
-        problem, sp, init = make_problem("cfg5", n, mesh=local)
-        # nu = 0.49 instead of cfg5's 0.4999: two Krylov solutions of the nearly incompressible system agree
-        # only to ~cond * rtol (1.5e-8 observed at rtol 1e-11), which would test MINRES, not the partition
-        problem.params["nu"] = 0.49
-        sp = dict(sp, direct_solver=False, krylov_rtol=1e-11, T=steps * sp["dt"])
+        problem, sp, init = make_problem(cfg, n, mesh=local)
+        sp = tune(problem, sp)
         solver = MPETSolver(problem, sp, device=rank, partition=Partition(rank, world))
         init(solver)
         for up, t in solver.solve():
@@ -48,9 +58,8 @@ def _worker(rank, world, port, n, results):
         owned = solver.partition.owned_dofs.astype(bool)
         # single-GPU reference on the same device (whole mesh)
         gmesh = BoxMesh(box[0], box[1], n, n, nz)
-        gproblem, gsp, ginit = make_problem("cfg5", n, mesh=gmesh)
-        gproblem.params["nu"] = 0.49
-        gsp = dict(gsp, direct_solver=False, krylov_rtol=1e-11, T=steps * gsp["dt"])
+        gproblem, gsp, ginit = make_problem(cfg, n, mesh=gmesh)
+        gsp = tune(gproblem, gsp)
         gsolver = MPETSolver(gproblem, gsp, device=rank)
         ginit(gsolver)
         for gup, gt in gsolver.solve():
@@ -90,3 +99,18 @@ def test_two_gpu_solution_matches_single_gpu():
         print(r, res)
         assert max(res["errs"]) < 1e-8, res      # north_star parity bar, per field, on owned dofs
         assert res["ghost"] < 1e-8               # ghosts are consistent copies
+
+
+def test_two_gpu_gmres_matches_single_gpu():
+    """Non-symmetric exchange coefficients -> restarted GMRES with all-reduced Gram-Schmidt coefficients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), 4, results, True), nprocs=2, join=True)
+    for r in range(2):
+        res = results[r]
+        print(r, res)
+        assert max(res["errs"]) < 1e-8, res
+        assert res["ghost"] < 1e-8

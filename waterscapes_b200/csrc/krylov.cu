@@ -223,12 +223,13 @@ __global__ void k_commit(int* __restrict__ fl) {
 template <int NV>
 __global__ void __launch_bounds__(kRedThreads)
 k_multidot(const double* __restrict__ V, int64_t ldv, const double* __restrict__ w, int64_t n,
-           double* __restrict__ partials /* [NV][gridDim] */) {
+           double* __restrict__ partials /* [NV][gridDim] */, const uint8_t* __restrict__ own) {
     __shared__ double sm[32];
     double s[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) s[k] = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (own && !own[i]) continue;              // multi-GPU: every dof is counted by its owner only
         double wi = w[i];
 #pragma unroll
         for (int k = 0; k < NV; ++k) s[k] += V[k * ldv + i] * wi;
@@ -447,23 +448,24 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
 static void multidot(mpet_ctx* ctx, KrylovWork* k, const double* V, int64_t ldv, int nv, const double* w,
                      double* hdev, int accumulate, cudaStream_t st) {
     const int G = 296;
+    const uint8_t* own = dist_owned_mask(ctx);
     for (int k0 = 0; k0 < nv; k0 += 4) {
         int c = std::min(4, nv - k0);
         const double* Vk = V + (int64_t)k0 * ldv;
         switch (c) {
-            case 1: k_multidot<1><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
-            case 2: k_multidot<2><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
-            case 3: k_multidot<3><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
-            default: k_multidot<4><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials); break;
+            case 1: k_multidot<1><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials, own); break;
+            case 2: k_multidot<2><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials, own); break;
+            case 3: k_multidot<3><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials, own); break;
+            default: k_multidot<4><<<G, kRedThreads, 0, st>>>(Vk, ldv, w, k->n, k->partials, own); break;
         }
         LAUNCH_CHECK(ctx);
         k_multifinal<<<c, kRedThreads, 0, st>>>(k->partials, G, hdev + k0, accumulate);
         LAUNCH_CHECK(ctx);
     }
+    dist_allreduce_sum(ctx, hdev, nv, st);       // no-op on one GPU (accumulate is only used with 0)
 }
 
 static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
-    MPET_REQUIRE(!dist_active(ctx), "multi-GPU GMRES is not built yet (MINRES is; S must be symmetric)");
     KrylovWork* k = get_work(ctx);
     const int64_t n = k->n;
     const int m = ctx->restart;
@@ -483,12 +485,10 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     double norm0 = -1, norm = 0, tol = 0;
     while (!converged && iters < ctx->maxit) {
         initial_residual(ctx, k, st);
-        pc_apply_flag(ctx, k->r, k->z, nullptr, st);
-        dot_to(ctx, k, k->z, k->z, nullptr, st);
-        k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev, nullptr);
-        LAUNCH_CHECK(ctx);
+        pc_apply_dist(ctx, k->r, k->z, nullptr, st);
+        dot_to(ctx, k, k->z, k->z, nullptr, st);          // k->red[0]: summed over owned dofs and all ranks
         double bb = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&bb, k->hdev, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&bb, k->red, sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         double beta = std::sqrt(bb);
         if (norm0 < 0) { norm0 = beta; tol = std::max(ctx->rtol * norm0, ctx->atol); }
@@ -502,7 +502,8 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         for (; j < m && iters < ctx->maxit; ++j) {
             double* w = V + (int64_t)(j + 1) * ldv;
             block_spmv(ctx, V + (int64_t)j * ldv, k->r, mask, nullptr, st);
-            pc_apply_flag(ctx, k->r, w, nullptr, st);
+            dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);      // ghost rows of the local matrix are incomplete
+            pc_apply_dist(ctx, k->r, w, nullptr, st);
             // classical Gram-Schmidt, two passes (CGS2)
             multidot(ctx, k, V, ldv, j + 1, w, k->hdev, 0, st);
             k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev, -1.0, n, w);
@@ -511,8 +512,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
             k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev + 128, -1.0, n, w);
             LAUNCH_CHECK(ctx);
             dot_to(ctx, k, w, w, nullptr, st);
-            k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->hdev + j + 1, nullptr);
-            LAUNCH_CHECK(ctx);
+            CUDA_CHECK(cudaMemcpyAsync(k->hdev + j + 1, k->red, sizeof(double), cudaMemcpyDeviceToDevice, st));
             std::vector<double> h1(j + 2), h2(j + 1);
             CUDA_CHECK(cudaMemcpyAsync(h1.data(), k->hdev, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(cudaMemcpyAsync(h2.data(), k->hdev + 128, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, st));
