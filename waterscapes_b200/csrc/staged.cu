@@ -105,7 +105,8 @@ constexpr size_t blk_smem_bytes() {
 
 // NR rows per node, NA scalar (pressure) column blocks.  U_OUT: rows are the displacement of a P2 node
 // (output = one padded 256-bit store), else the pressures of a vertex (NR scalar stores, stride nv).
-template <int NR, int NA, bool U_OUT, class CFG>
+// LANES lanes of a warp share one node (32 / LANES nodes per warp step).
+template <int NR, int NA, bool U_OUT, int LANES, class CFG>
 __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks)
 k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase gbase,
                   const int32_t* __restrict__ rpA, const int32_t* __restrict__ colA,
@@ -114,14 +115,15 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
                   int64_t n2, int64_t nv, const uint8_t* __restrict__ mask, const int* __restrict__ done,
                   int contiguous) {
     if (done && *done) return;
-    constexpr int kStages = CFG::kStages, NCW = CFG::kConsumers;
+    constexpr int kStages = CFG::kStages, NCW = CFG::kConsumers, GPW = 32 / LANES;
     using Stage = BlockStage<NR, blk_capv(CFG::kCapV, NR)>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage* stage = reinterpret_cast<Stage*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(Stage));
     uint64_t* empty = full + kStages;
     BlockChunk* desc = reinterpret_cast<BlockChunk*>(empty + kStages);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int gw = wl / LANES, lane = wl % LANES;          // node slot inside the warp, lane inside the slot
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
@@ -142,7 +144,7 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
 
     if (warp == 0) {
         // ------------------------------------------------ producer: one thread feeds the copy engine
-        if (lane != 0) return;
+        if (wl != 0) return;
         for (int it = 0; it < nmine; ++it) {
             const int s = it % kStages;
             if (it >= kStages) mbar_wait(&empty[s], (uint32_t)((it / kStages - 1) & 1));
@@ -172,9 +174,9 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
         return;
     }
 
-    // ---------------------------------------------------- consumers: one warp per node, dealt round-robin
+    // ---------------------------------------------------- consumers: node slots dealt round-robin across chunks
     const int cw = warp - 1;
-    int rot = 0;                               // nodes of earlier chunks, modulo NCW
+    int rot = 0;                               // warp steps (GPW nodes each) of earlier chunks, modulo NCW
     for (int it = 0; it < nmine; ++it) {
         const int s = it % kStages;
         mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
@@ -187,17 +189,21 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
 #pragma unroll
         for (int g = 0; g < NR; ++g) vsk[g] = (int)((gbase.v[g] + c.v_rel) & 1);
 
-        int nl = cw - rot;
-        if (nl < 0) nl += NCW;
-        for (; nl < c.nn; nl += NCW) {
-            const int32_t ra = S.rpA[rsk + nl], rb = S.rpB[rsk + nl];
-            const int dA = S.rpA[rsk + nl + 1] - ra, dB = S.rpB[rsk + nl + 1] - rb;
+        const int nq = (c.nn + GPW - 1) / GPW;
+        int q = cw - rot;
+        if (q < 0) q += NCW;
+        for (; q < nq; q += NCW) {
+            const int nl = q * GPW + gw;
+            const bool active = nl < c.nn;
+            const int nls = active ? nl : 0;
+            const int32_t ra = S.rpA[rsk + nls], rb = S.rpB[rsk + nls];
+            const int dA = active ? S.rpA[rsk + nls + 1] - ra : 0, dB = active ? S.rpB[rsk + nls + 1] - rb : 0;
             const int eA = ra - a_base + ska, eB = rb - b_base + skb;
             const int rel = 3 * (ra - a_base) + NA * (rb - b_base);
-            const int64_t node = (int64_t)c.n0 + nl;
+            const int64_t node = (int64_t)c.n0 + nls;
             // every global load of the node's first sweep is issued before anything is consumed
             uint32_t mword = 0;
-            if (U_OUT && mask && lane == 0) mword = __ldg(reinterpret_cast<const uint32_t*>(mask + 4 * node));
+            if (U_OUT && mask && lane == 0 && active) mword = __ldg(reinterpret_cast<const uint32_t*>(mask + 4 * node));
             const bool hasA = lane < dA, hasB = (NA > 0) && lane < dB;
             d4 xv = {0, 0, 0, 0};
             if (hasA) xv = ld256_gather(x + 4 * (int64_t)S.colA[eA + lane]);
@@ -224,7 +230,7 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
 #pragma unroll
                     for (int g = 0; g < NR; ++g) acc[g] += S.vals[g][vsk[g] + rel + 3 * dA + i * dB + lane] * pv[i];
             }
-            for (int j = lane + 32; j < dA; j += 32) {            // nodes with more than 32 neighbours
+            for (int j = lane + LANES; j < dA; j += LANES) {       // nodes with more than LANES neighbours
                 const d4 xw = ld256_gather(x + 4 * (int64_t)S.colA[eA + j]);
 #pragma unroll
                 for (int g = 0; g < NR; ++g) {
@@ -233,7 +239,7 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
                 }
             }
             if (NA > 0) {
-                for (int j = lane + 32; j < dB; j += 32) {
+                for (int j = lane + LANES; j < dB; j += LANES) {
                     const int32_t col = S.colB[eB + j];
 #pragma unroll
                     for (int i = 0; i < NA; ++i) {
@@ -246,9 +252,9 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
 #pragma unroll
             for (int g = 0; g < NR; ++g) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o);
+                for (int o = LANES / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, LANES);
             }
-            if (lane == 0) {
+            if (lane == 0 && active) {
                 if (U_OUT) {
                     d4 out = {acc[0], NR > 1 ? acc[NR > 1 ? 1 : 0] : 0.0, NR > 2 ? acc[NR > 2 ? 2 : 0] : 0.0, 0.0};
                     if (mask) {
@@ -270,9 +276,9 @@ k_block_rows_pipe(const BlockChunk* __restrict__ chunks, int nchunks, GroupBase 
                 }
             }
         }
-        rot = (rot + c.nn) % NCW;
+        rot = (rot + nq) % NCW;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);      // this warp is done reading stage s
+        if (wl == 0) mbar_arrive(&empty[s]);      // this warp is done reading stage s
     }
 }
 
@@ -469,12 +475,12 @@ T* upload_vec(mpet_ctx* ctx, const std::vector<T>& h) {
     return d;
 }
 
-template <int NR, int NA, bool U_OUT, class CFG>
-void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
-                       const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
-                       cudaStream_t st) {
+template <int NR, int NA, bool U_OUT, int LANES, class CFG>
+void launch_block_rows_l(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
+                         const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
+                         cudaStream_t st) {
     constexpr size_t smem = blk_smem_bytes<NR, CFG>();
-    auto kern = k_block_rows_pipe<NR, NA, U_OUT, CFG>;
+    auto kern = k_block_rows_pipe<NR, NA, U_OUT, LANES, CFG>;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -484,6 +490,19 @@ void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, c
     kern<<<grid, CFG::kThreads, smem, st>>>(P.chunks, P.nchunks, gb, gA.rowptr, gA.col, gB.rowptr, gB.col, ctx->vals, x,
                                             y, ctx->N2, ctx->Nv, mask, done, env_cfg("MPET_BLK_ORDER", 2, 0));
     LAUNCH_CHECK(ctx);
+}
+
+// lanes per node: the displacement rows (28 node neighbours on average) and the pressure rows (63)
+template <int NR, int NA, bool U_OUT, class CFG>
+void launch_block_rows(mpet_ctx* ctx, const BlockPlan& P, const GroupBase& gb, const NodeGraph& gA,
+                       const NodeGraph& gB, const double* x, double* y, const uint8_t* mask, const int* done,
+                       cudaStream_t st) {
+    // measured on cfg5 (spmv incl. layout conversions): 32/32 lanes 2.037 ms, 16 (u rows) / 32 (p rows) 1.885 ms,
+    // 16/16 1.922 ms, 32/16 2.072 ms: half a warp per P2 node halves the shuffle work per node
+    const int lanes = env_cfg(U_OUT ? "MPET_BLK_LANES_U" : "MPET_BLK_LANES_P", 64, U_OUT ? 16 : 32);
+    if (lanes == 8) launch_block_rows_l<NR, NA, U_OUT, 8, CFG>(ctx, P, gb, gA, gB, x, y, mask, done, st);
+    else if (lanes == 16) launch_block_rows_l<NR, NA, U_OUT, 16, CFG>(ctx, P, gb, gA, gB, x, y, mask, done, st);
+    else launch_block_rows_l<NR, NA, U_OUT, 32, CFG>(ctx, P, gb, gA, gB, x, y, mask, done, st);
 }
 
 template <int NA, class CFG>
