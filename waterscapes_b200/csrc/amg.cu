@@ -1059,6 +1059,10 @@ void finish_hierarchy(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
         for (auto& L : H.levels) fprintf(stderr, " %lld rows/%lld nnz", (long long)L.A.nrows, (long long)L.A.nnz);
         fprintf(stderr, " | coarse %s (%lld)\n", H.coarse_inv ? "dense inverse" : "Chebyshev", (long long)H.levels.back().A.nrows);
     }
+    if (H.poly_degree == 0) {     // work vectors of multi-cycle applications (owned by the hierarchy's arena)
+        H.cyc_r = dev_alloc<double>(ctx, H.levels[0].A.nrows * H.nrhs);
+        H.cyc_e = dev_alloc<double>(ctx, H.levels[0].A.nrows * H.nrhs);
+    }
     for (auto& L : H.levels) {
         alloc_level_work(ctx, L, H.nrhs);
         L.lambda_max = estimate_lambda_max(ctx, L, st);
@@ -1224,10 +1228,6 @@ static void cycles(mpet_ctx* ctx, AmgHierarchy& H, int ncycles, const double* b,
     vcycle<W>(ctx, H, 0, b, x, done, st);
     AmgLevel& L = H.levels[0];
     for (int c = 1; c < ncycles; ++c) {
-        if (!H.cyc_r) {
-            H.cyc_r = dev_alloc<double>(ctx, L.A.nrows * W);
-            H.cyc_e = dev_alloc<double>(ctx, L.A.nrows * W);
-        }
         launch_epi<W, EPI_RESID>(ctx, L.A, L.planA, x, b, H.cyc_r, nullptr, nullptr, 0, 0, done, st);
         if (L.halo_plan >= 0) dist_halo(ctx, L.halo_plan, H.cyc_r, false, done, st);
         vcycle<W>(ctx, H, 0, H.cyc_r, H.cyc_e, done, st);
