@@ -360,7 +360,7 @@ def main():
     spmv_ms = prof["spmv"]["ms"] / max(1, prof["spmv"]["count"])
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_spmv_block_u + k_spmv_block_p (node-blocked SpMV of the block system inside MINRES)",
+    roofline = {"bound": "hbm", "kernel": "k_block_rows_pipe<3,A,1> + <A,A,0> (node-blocked SpMV of the block system inside MINRES, staged.cu)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "csr_equivalent_gbs": csr_equiv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
