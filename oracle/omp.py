@@ -22,6 +22,10 @@ def lib():
         L.oracle_csr_spmm.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_csr_spmm.restype = None
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_assemble_lhs_tet.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_assemble_lhs_tet.restype = None
         _lib = L
     return _lib
 
@@ -69,3 +73,45 @@ def parallelise(block_amg):
             if L.P is not None:
                 L.P = OmpCsr(L.P, with_transpose=True)
     return block_amg
+
+
+class LhsAssembler:
+    """``assemble(a)`` of the standard formulation as an OpenMP cell loop (oracle/csrc/cpu_kernels.c), on the
+    oracle's own pattern.  Same numbers as ``MPETOracle.assemble_lhs`` without Robin / nullspace terms (checked in
+    tests/test_oracle_krylov.py); exists so that the CPU timing arm is not dominated by numpy's assembly."""
+
+    def __init__(self, o):
+        import scipy.sparse as sp
+        from .fem import simplex_quadrature, tabulate
+        from .mpet import convert_to_mu_lmbda
+        assert o.d == 3 and o.P_SHIFT == 0 and o.space.nreal == 0 and o.space.perm is None
+        self.o = o
+        self.rowptr, self.cols = o.pattern()
+        self.rowptr = np.ascontiguousarray(self.rowptr, dtype=np.int64)
+        self.cols = np.ascontiguousarray(self.cols, dtype=np.int32)
+        pts, wts = simplex_quadrature(3, 2)
+        _, dN2 = tabulate(3, 2, pts)
+        N1, dN1 = tabulate(3, 1, pts)
+        self.nq = len(wts)
+        self.dN2 = np.ascontiguousarray(dN2, dtype=np.float64)          # [nq, 10, 3]
+        self.N1 = np.ascontiguousarray(N1, dtype=np.float64)            # [nq, 4]
+        self.dN1 = np.ascontiguousarray(dN1[0], dtype=np.float64)       # [4, 3] (constant)
+        self.wq = np.ascontiguousarray(wts, dtype=np.float64)
+        self.cells = np.ascontiguousarray(o.mesh.cells, dtype=np.int64)
+        self.cell_dofs = np.ascontiguousarray(o.space.cell_dofs, dtype=np.int64)
+        self.coords = np.ascontiguousarray(o.mesh.coords, dtype=np.float64)
+        self._sp = sp
+        self._lame = convert_to_mu_lmbda
+
+    def __call__(self):
+        o = self.o
+        mu, lmbda = self._lame(o.E, o.nu)
+        coef = np.ascontiguousarray(np.concatenate([[mu, lmbda, o.dt * o.theta], o.alpha, o.c, o.K,
+                                                    np.asarray(o.S, dtype=float).ravel()]), dtype=np.float64)
+        vals = np.zeros(self.cols.shape[0])
+        p = lambda a: a.ctypes.data
+        lib().oracle_assemble_lhs_tet(self.cells.shape[0], p(self.cells), p(self.cell_dofs), o.A, p(self.coords),
+                                      self.nq, p(self.dN2), p(self.N1), p(self.dN1), p(self.wq), p(coef),
+                                      p(self.rowptr), p(self.cols), p(vals))
+        N = o.space.N
+        return self._sp.csr_matrix((vals, self.cols, self.rowptr.astype(np.int32)), shape=(N, N))

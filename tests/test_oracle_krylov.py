@@ -1,5 +1,6 @@
 """CPU: the oracle's MINRES + block-AMG restatement agrees with its own direct solve."""
 import numpy as np
+import pytest
 import scipy.sparse.linalg as spla
 
 from oracle.mesh import unit_cube_mesh
@@ -99,3 +100,17 @@ def test_drop_small_preserves_row_sums_and_symmetry():
     assert np.allclose(np.asarray(D.sum(axis=1)).ravel(), np.asarray(A.sum(axis=1)).ravel())
     assert abs(D - D.T).max() < 1e-14
     assert np.all(np.linalg.eigvalsh(D.toarray()) > 0)
+
+
+@pytest.mark.parametrize("A", [1, 2, 3])
+def test_openmp_cell_loop_matches_numpy_assembly(A):
+    """oracle/csrc/cpu_kernels.c:oracle_assemble_lhs_tet (the CPU timing arm's assemble(a)) == the numpy
+    restatement, to round-off, on a jittered mesh."""
+    from oracle import omp
+    from tests.test_gpu_assembly import PARAMS
+    mesh = unit_cube_mesh(3, jitter=0.2)
+    o = MPETOracle(mesh, PARAMS[A], dt=0.05, theta=0.5)
+    ref = o.on_pattern(o.assemble_lhs())
+    got = omp.LhsAssembler(o)()
+    assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.indptr, ref.indptr)
+    assert np.linalg.norm(got.data - ref.data) / np.linalg.norm(ref.data) < 1e-14
