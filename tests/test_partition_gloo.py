@@ -106,7 +106,7 @@ def _worker(rank, world, port, n, results):
 @pytest.mark.parametrize("world,n", [(2, 6), (4, 12)])
 def test_partition_and_halo_lists(world, n):
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # no fork of a process that already runs OpenMP threads
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, results), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world))
