@@ -192,7 +192,7 @@ def run_cpu(config, n, rtol, steps, warmup, maxit):
     from oracle import omp
     from threadpoolctl import threadpool_limits
     threadpool_limits(1, user_api="blas")       # numpy's BLAS pool would fight the OpenMP row loops for the cores
-    threads = omp.num_threads()
+    threads = omp.use_all_cores()
     o = build_oracle_problem(config, n)
     dofs, _ = o.dirichlet(o.t)
     M = omp.parallelise(BlockAMG(o, dofs))      # hierarchy set-up is outside the step on both arms

@@ -52,6 +52,15 @@ double oracle_dot(int64_t n, const double* x, const double* y) {
     return s;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and takes the cores back */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

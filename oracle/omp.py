@@ -34,6 +34,14 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def use_all_cores():
+    """Run the OpenMP loops on every core this process may use (torchrun sets OMP_NUM_THREADS=1 for its ranks;
+    the CPU timing arm runs on rank 0 alone).  Returns the thread count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 class OmpCsr:
     def __init__(self, A, with_transpose=False):
         A = A.tocsr()
