@@ -58,3 +58,24 @@ def test_sizes_formula():
     s = sizes(71, 4)
     assert s["dofs"] == 10265613 and s["nnz"] == 1400017525 and s["cells"] == 2147466
     p = Parameters("x"); p.add("dt", 0.1); p.update(dict(dt=0.2)); assert p["dt"] == 0.2
+
+
+def test_elastic_stress_of_a_quadratic_field():
+    """mpetproblem.py:18-24 mirror: sigma = 2 mu eps(u) + lambda div(u) I, exact for P2 displacements."""
+    from waterscapes_b200.mpet.dolfin_shim import FunctionSpace, SubFunction
+    from waterscapes_b200.mpet.mpetproblem import elastic_stress
+    mesh = UnitCubeMesh(2)
+    space = FunctionSpace.from_host(mesh, 1)
+    X = space.node2_coordinates()
+    u = np.stack([X[:, 0] ** 2 + 2 * X[:, 1], X[:, 1] * X[:, 2], 3 * X[:, 2] - X[:, 0]], axis=1)
+    E, nu = 10.0, 0.3
+    mu, lm = convert_to_mu_lmbda(E, nu)
+    sig = elastic_stress(SubFunction(space, 0, u), E, nu).cell_values()
+    xc = mesh.coordinates[mesh.cells].mean(axis=1)
+    grad = np.zeros((xc.shape[0], 3, 3))
+    grad[:, 0, 0] = 2 * xc[:, 0]; grad[:, 0, 1] = 2.0
+    grad[:, 1, 1] = xc[:, 2]; grad[:, 1, 2] = xc[:, 1]
+    grad[:, 2, 2] = 3.0; grad[:, 2, 0] = -1.0
+    eps = 0.5 * (grad + np.swapaxes(grad, 1, 2))
+    ref = 2 * mu * eps + lm * np.trace(grad, axis1=1, axis2=2)[:, None, None] * np.eye(3)
+    assert np.allclose(sig, ref, rtol=1e-12, atol=1e-12)

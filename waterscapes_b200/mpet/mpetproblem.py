@@ -1,5 +1,7 @@
 """MPETProblem: the reference's problem container, unchanged surface
 (src/mpet/mpet/mpetproblem.py:8-24 Lame conversions, :103-180 class)."""
+import numpy as np
+
 from .dolfin_shim import Constant, MeshFunction, INVALID
 
 
@@ -15,6 +17,41 @@ def convert_to_mu_lmbda(E, nu):
     mu = E / (2.0 * ((1.0 + nu)))
     lmbda = nu * E / ((1.0 - 2.0 * nu) * (1.0 + nu))
     return (mu, lmbda)
+
+
+class CellTensorField(object):
+    """Per-cell evaluation of a tensor built from the gradient of a split P2 displacement (host side,
+    post-processing only): ``cell_values()`` -> [Nc, 3, 3] at the cell barycentres."""
+
+    def __init__(self, u, two_mu, lmbda):
+        self.u, self.two_mu, self.lmbda = u, two_mu, lmbda
+
+    def cell_values(self):
+        sp = self.u.space
+        mesh = sp.mesh
+        cells = mesh.cells.astype(np.int64)
+        x = mesh.coordinates[cells]                                     # [Nc, 4, 3]
+        J = np.swapaxes(x[:, 1:, :] - x[:, :1, :], 1, 2)                # d x_i / d X_j
+        Jinv = np.linalg.inv(J)
+        lam = np.full(4, 0.25)                                          # barycentre
+        gl = np.array([[-1.0, -1.0, -1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+        le = [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)]           # UFC local edges
+        dphi = [(4 * lam[i] - 1) * gl[i] for i in range(4)] + [4 * (lam[a] * gl[b] + lam[b] * gl[a]) for a, b in le]
+        dphi = np.asarray(dphi)                                         # [10, 3] reference gradients
+        nodes = np.concatenate([cells] + [sp.Nv + sp.edge_index(cells[:, a], cells[:, b])[:, None]
+                                          for a, b in le], axis=1)       # [Nc, 10]
+        g = np.einsum("ak,ckm->cam", dphi, Jinv)                        # physical gradients
+        grad_u = np.einsum("cai,cam->cim", self.u.values[nodes], g)     # d u_i / d x_m
+        eps = 0.5 * (grad_u + np.swapaxes(grad_u, 1, 2))
+        div = np.trace(grad_u, axis1=1, axis2=2)
+        return self.two_mu * eps + self.lmbda * div[:, None, None] * np.eye(3)[None]
+
+
+def elastic_stress(u, E, nu):
+    """mpetproblem.py:18-24: sigma(u) = 2 mu eps(u) + lambda div(u) I for a split displacement ``u``
+    (``up.split()[0]``); evaluated per cell on the host (post-processing, not on the timestep path)."""
+    (mu, lmbda) = convert_to_mu_lmbda(float(E), float(nu))
+    return CellTensorField(u, 2.0 * mu, lmbda)
 
 
 class MPETProblem(object):
