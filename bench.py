@@ -149,9 +149,10 @@ def build_oracle_problem(config, n):
              np.sin(pi * x[:, 0]) * np.sin(pi * x[:, 1]) * np.cos(pi * x[:, 2])], 1) * np.sin(pi * t))
         o.p_bar = [Coef(fn=lambda x, t, i=i: (i + 1) * np.sin(pi * x[:, 0]) * np.cos(pi * x[:, 1])
                         * np.sin(pi * x[:, 2]) * np.sin(2 * pi * t)) for i in range(2)]
-        o.f = Coef(fn=lambda x, t: np.stack([np.sin(pi * x[:, 0]) * np.sin(pi * t), np.cos(pi * x[:, 1]) * np.sin(pi * t),
-                                             x[:, 2] * np.sin(pi * t)], 1), degree=2)
-        o.g = [Coef(fn=lambda x, t, i=i: (i + 1) * np.cos(pi * x[:, 0]) * np.cos(2 * pi * t), degree=1) for i in range(2)]
+        from waterscapes_b200.mms import cfg1_exact, standard_sources      # input data only (sympy), no engine
+        mms = standard_sources(params, *cfg1_exact())
+        o.f = Coef(fn=mms["f"], degree=2)
+        o.g = [Coef(fn=mms["g"][i], degree=1) for i in range(2)]
         o.momentum_markers[:] = 0
         for i in range(2):
             o.continuity_markers[i][:] = 0

@@ -123,9 +123,13 @@ int mpet_csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr_dev, const
  * pc    : 0 = none, 1 = Jacobi, 2 = block-diagonal AMG V-cycle (needs mpet_assemble_prec first).
  * mpet_pc_setup builds the AMG hierarchies from the current P (once per dt).
  * mpet_solve: x_dev holds the initial guess on entry (Dirichlet entries are overwritten with the
- * boundary values), the solution on exit.  Convergence: ||r||_{M^-1} <= max(rtol*||r0||_{M^-1}, atol)
- * (PETSc's default preconditioned-norm test).  Synchronous.  info_host[0] = iterations,
- * [1] = converged flag, [2] = final relative residual, [3] = initial residual norm. */
+ * boundary values), the solution on exit.  Convergence: ||r||_B <= max(rtol*||b||_B, atol) with b the
+ * right-hand side after apply_symmetric (bc_symmetric.py:11-22) and B the preconditioner -- PETSc's default
+ * test for a nonzero initial guess (KSPConvergedDefault: reference norm = preconditioned norm of b, not of
+ * the initial residual); MINRES also stops when the residual norm fell by < 1 % over 256 iterations
+ * (stagnation at round-off).  Synchronous.  info_host f64[8]: [0] iterations, [1] converged flag,
+ * [2] final ||r||_B / ||b||_B, [3] initial residual norm, [4] breakdown flag (indefinite preconditioner),
+ * [5] reason (2 tolerance reached, -3 iteration limit, -4 breakdown, -5 stagnation), [6] ||b||_B. */
 int mpet_krylov_setup(mpet_ctx* ctx, int method, int pc, double rtol, double atol, int maxit,
                       int restart);
 int mpet_pc_setup(mpet_ctx* ctx, void* stream);

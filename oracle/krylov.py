@@ -6,8 +6,10 @@ restated with scipy.sparse matvecs:
 
 * ``minres``: PETSc's KSPMINRES recurrence [EXT: petsc/src/ksp/ksp/impls/minres/minres.c], one operator
   and one preconditioner application per iteration, convergence test on the preconditioned norm
-  ``|eta| <= max(rtol * |eta_0|, atol)``, Dirichlet rows handled as in ``apply_symmetric``
-  (bc_symmetric.py:11-22).
+  ``|eta| <= max(rtol * ||b||_B, atol)`` with b the right-hand side after ``apply_symmetric``
+  (bc_symmetric.py:11-22) -- PETSc's KSPConvergedDefault takes the norm of b, not of the initial residual,
+  as reference when the initial guess is nonzero [EXT: petsc/src/ksp/ksp/interface/iterativ.c] --,
+  Dirichlet rows handled as in ``apply_symmetric``; stagnation exit as in krylov.cu.
 * ``BlockAMG``: the block-diagonal V-cycle of DESIGN.md section "Preconditioner" (hypre BoomerAMG itself is
   an un-vendored dependency; its defaults are not reproducible here).  This class restates, loop for
   loop, the hierarchy the CUDA library builds (p-coarsening P2 -> P1, greedy smoothed aggregation,
@@ -33,6 +35,8 @@ P1_DEGREE = 4
 COARSE_MAX = 300
 DENSE_MAX = 700
 MAX_LEVELS = 12
+STAG_WINDOW = 256      # krylov.cu: kStagWindow / kStagFactor
+STAG_FACTOR = 0.99
 
 
 # ------------------------------------------------------------------------------------------ MINRES
@@ -56,10 +60,19 @@ def minres(A, b, x0, M, mask=None, rtol=1e-5, atol=1e-50, maxit=10000):
         raise RuntimeError("indefinite preconditioner")
     beta = np.sqrt(dp)
     norm0 = beta
-    tol = max(rtol * beta, atol)
-    info = dict(niter=0, converged=False, res0=norm0, rel_res=1.0)
+    # reference norm: sqrt(b . B b) of the symmetrically eliminated right-hand side
+    if mask is not None:
+        xb = np.where(mask, x, 0.0)
+        rb = np.where(free, b - A @ xb, xb)
+    else:
+        rb = b
+    dpb = float(rb @ M(rb))
+    bnorm = np.sqrt(dpb) if dpb > 0 else beta
+    tol = max(rtol * bnorm, atol)
+    stag_ref = 1e300
+    info = dict(niter=0, converged=False, res0=norm0, rel_res=1.0, bnorm=bnorm, reason=-3)
     if beta <= tol or beta == 0.0:
-        info.update(converged=True, rel_res=0.0 if beta == 0 else 1.0)
+        info.update(converged=True, rel_res=0.0 if beta == 0 else beta / bnorm, reason=2)
         return x, info
     eta = beta
     c = c_old = 1.0
@@ -93,10 +106,16 @@ def minres(A, b, x0, M, mask=None, rtol=1e-5, atol=1e-50, maxit=10000):
         if beta != 0.0:
             v, u = r / beta, z / beta
         info["niter"] = it
-        info["rel_res"] = abs(eta) / norm0
+        info["rel_res"] = abs(eta) / bnorm
         if abs(eta) <= tol:
             info["converged"] = True
+            info["reason"] = 2
             break
+        if it % STAG_WINDOW == 0:
+            if abs(eta) > STAG_FACTOR * stag_ref:
+                info["reason"] = -5
+                break
+            stag_ref = abs(eta)
         if beta == 0.0:
             break
     return x, info

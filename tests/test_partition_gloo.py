@@ -35,27 +35,45 @@ def _global_node_index(o_global, keys, nvg):
     return order[pos]
 
 
-def _worker(rank, world, port, n, results):
+def _worker(rank, world, port, n, results, mode="slab"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from waterscapes_b200.parallel import extract_local, box_slab, Partition, node_global_keys
+        from waterscapes_b200.parallel import (extract_local, box_slab, box_brick, brick_grid, rcb_partition, Partition,
+                                               node_global_keys)
         from waterscapes_b200.mpet.dolfin_shim import FunctionSpace, UnitCubeMesh
-        g = unit_cube_mesh(n)
+        g = unit_cube_mesh(n, jitter=0.2 if mode == "rcb" else 0.0)
         J = PARAMS["J"]
-        # cell partition into z-slabs by cell index (cells are ordered layer by layer, 6 n^2 per layer)
-        layer = np.arange(g.num_cells) // (6 * n * n)
-        bounds = [(n * r) // world for r in range(world + 1)]
-        cell_owner = np.searchsorted(np.asarray(bounds[1:]), layer, side="right").astype(np.int64)
-        local = extract_local(g.coords, g.cells, cell_owner, rank)
-        slab = box_slab((0, 0, 0), (1, 1, 1), n, n, n, rank, world)
-        assert np.array_equal(slab.global_vertex[slab.cells], local.global_vertex[local.cells])
-        assert np.allclose(slab.coordinates, local.coordinates)
-        assert np.array_equal(slab.cell_owner, local.cell_owner)
-        # artificial (cut) facets carry no boundary: both constructions agree and none lies inside the cube
-        fs, fl = slab.exterior_facets(), local.exterior_facets()
-        assert np.array_equal(fs["vertices"], fl["vertices"])
+        if mode == "slab":
+            # cell partition into z-slabs by cell index (cells are ordered layer by layer, 6 n^2 per layer)
+            layer = np.arange(g.num_cells) // (6 * n * n)
+            bounds = [(n * r) // world for r in range(world + 1)]
+            cell_owner = np.searchsorted(np.asarray(bounds[1:]), layer, side="right").astype(np.int64)
+            local = extract_local(g.coords, g.cells, cell_owner, rank)
+            slab = box_slab((0, 0, 0), (1, 1, 1), n, n, n, rank, world)
+            assert np.array_equal(slab.global_vertex[slab.cells], local.global_vertex[local.cells])
+            assert np.allclose(slab.coordinates, local.coordinates)
+            assert np.array_equal(slab.cell_owner, local.cell_owner)
+            # artificial (cut) facets carry no boundary: both constructions agree
+            fs, fl = slab.exterior_facets(), local.exterior_facets()
+            assert np.array_equal(fs["vertices"], fl["vertices"])
+            brick = box_brick((0, 0, 0), (1, 1, 1), n, n, n, rank, world, grid=(1, 1, world))
+            assert np.array_equal(brick.global_vertex[brick.cells], slab.global_vertex[slab.cells])
+        elif mode == "brick":
+            # 3-D bricks: corner ghosts are touched by up to 8 ranks
+            assert brick_grid(8) == (2, 2, 2) and brick_grid(4) == (1, 2, 2) and brick_grid(2) == (1, 1, 2)
+            local = box_brick((0, 0, 0), (1, 1, 1), n, n, n, rank, world)
+            own_cells = torch.tensor([int((local.cell_owner == rank).sum())], dtype=torch.int64)
+            dist.all_reduce(own_cells)
+            assert int(own_cells) == g.num_cells                # the bricks tile the box
+        else:
+            # unstructured route: recursive coordinate bisection of the centroids of a jittered mesh
+            cell_owner = rcb_partition(g.coords[g.cells].mean(axis=1), world)
+            assert np.bincount(cell_owner, minlength=world).min() >= g.num_cells // world - 1
+            local = extract_local(g.coords, g.cells, cell_owner, rank)
+        fl = local.exterior_facets()
+        # none of the remaining local-exterior facets lies inside the cube
         xm = local.coordinates[fl["vertices"]].mean(axis=1)
         on_bnd = (np.abs(xm) < 1e-12).any(axis=1) | (np.abs(xm - 1) < 1e-12).any(axis=1)
         assert on_bnd.all()
@@ -103,10 +121,10 @@ def _worker(rank, world, port, n, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 6), (4, 12)])
-def test_partition_and_halo_lists(world, n):
+@pytest.mark.parametrize("world,n,mode", [(2, 6, "slab"), (4, 12, "slab"), (4, 6, "brick"), (8, 6, "brick"), (3, 5, "rcb")])
+def test_partition_and_halo_lists(world, n, mode):
     port = _free_port()
     mgr = mp.get_context("spawn").Manager()      # no fork of a process that already runs OpenMP threads
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, port, n, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, results, mode), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world))

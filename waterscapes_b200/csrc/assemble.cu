@@ -83,6 +83,12 @@ Poly dphi2(int a, int m) {
 bool g_tables_ready = false;
 
 // ---- device ------------------------------------------------------------------------------------
+// coefficient tables travel as a kernel argument (by value): no per-assembly cudaMalloc / copy / sync
+struct AsmCoefs {
+    double cup[MPET_MAX_NETWORKS], cpu[MPET_MAX_NETWORKS], cl[MPET_MAX_NETWORKS];
+    double cm[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
+};
+
 __global__ void k_geometry(const double* __restrict__ coords, const int32_t* __restrict__ cells,
                            int64_t nc, double* __restrict__ geom) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -214,7 +220,9 @@ k_asm21(const int32_t* __restrict__ rp21, const int32_t* __restrict__ col21,
         const double* __restrict__ geom, const int32_t* __restrict__ rp22,
         const int32_t* __restrict__ rp12, const int32_t* __restrict__ t21to12,
         const int64_t* __restrict__ rowptr, int64_t n2, int64_t nv, int64_t nnz21, int A,
-        const double* __restrict__ cup, const double* __restrict__ cpu, double* __restrict__ vals) {
+        const AsmCoefs K, double* __restrict__ vals) {
+    const double* cup = K.cup;
+    const double* cpu = K.cpu;
     __shared__ double sQ[120];
     for (int i = threadIdx.x; i < 120; i += blockDim.x) sQ[i] = c_Q21[i];
     __syncthreads();
@@ -256,8 +264,10 @@ __global__ void __launch_bounds__(256)
 k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
         const uint32_t* __restrict__ glist, const double* __restrict__ geom,
         const int32_t* __restrict__ rp12, const int64_t* __restrict__ rowptr, int64_t n2, int64_t nv,
-        int64_t nnz11, int A, const double* __restrict__ cm, const double* __restrict__ cl,
-        double* __restrict__ vals, double* __restrict__ m11, double* __restrict__ l11) {
+        int64_t nnz11, int A, const AsmCoefs K, double* __restrict__ vals, double* __restrict__ m11,
+        double* __restrict__ l11) {
+    const double* cm = K.cm;
+    const double* cl = K.cl;
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz11) return;
     int64_t v = row_of_entry(rp11, nv, (int32_t)e);
@@ -297,8 +307,9 @@ k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
 }
 
 __global__ void k_prec11(const double* __restrict__ m11, const double* __restrict__ l11, int64_t nnz11,
-                         int A, const double* __restrict__ cm, const double* __restrict__ ck,
-                         double* __restrict__ pp11) {
+                         int A, const AsmCoefs K, double* __restrict__ pp11) {
+    const double* cm = K.cup;      // slots re-used: pm in cup, pk in cpu
+    const double* ck = K.cpu;
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz11) return;
     double M = m11[e], L = l11[e];
@@ -344,24 +355,14 @@ static int asm22_grid(mpet_ctx* ctx, int64_t n2) {
     return (int)std::min<int64_t>(grid_for(n2 * 32, 256), (int64_t)ctx->sm_count * 4);
 }
 
-static double* upload_small(mpet_ctx* ctx, const double* h, int n, cudaStream_t st, std::vector<void*>& tmp) {
-    double* d = nullptr;
-    CUDA_CHECK(cudaMalloc(&d, sizeof(double) * (n > 0 ? n : 1)));
-    tmp.push_back(d);
-    CUDA_CHECK(cudaMemcpyAsync(d, h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    return d;
-}
-
 void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
     MPET_REQUIRE(ctx->params_set, "mpet_set_params must be called before assembly");
     const int A = ctx->A;
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
     const BlockCoefs& C = ctx->coef;
-    std::vector<void*> tmp;
-    double* d_cup = upload_small(ctx, C.cup, A, st, tmp);
-    double* d_cpu = upload_small(ctx, C.cpu, A, st, tmp);
-    double* d_cm = upload_small(ctx, C.cm, A * A, st, tmp);
-    double* d_cl = upload_small(ctx, C.cl, A, st, tmp);
+    AsmCoefs K;
+    for (int i = 0; i < MPET_MAX_NETWORKS; ++i) { K.cup[i] = C.cup[i]; K.cpu[i] = C.cpu[i]; K.cl[i] = C.cl[i]; }
+    for (int i = 0; i < MPET_MAX_NETWORKS * MPET_MAX_NETWORKS; ++i) K.cm[i] = C.cm[i];
 
     const int threads = 256;
     if (ctx->k22) {
@@ -377,15 +378,13 @@ void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
     if (A > 0) {
         k_asm21<<<grid_for(ctx->g21.nnz, threads), threads, 0, st>>>(
             ctx->g21.rowptr, ctx->g21.col, ctx->g21.gptr, ctx->g21.glist, ctx->geom, ctx->g22.rowptr,
-            ctx->g12.rowptr, ctx->t21to12, ctx->rowptr, n2, nv, ctx->g21.nnz, A, d_cup, d_cpu, ctx->vals);
+            ctx->g12.rowptr, ctx->t21to12, ctx->rowptr, n2, nv, ctx->g21.nnz, A, K, ctx->vals);
         LAUNCH_CHECK(ctx);
         k_asm11<<<grid_for(ctx->g11.nnz, threads), threads, 0, st>>>(
             ctx->g11.rowptr, ctx->g11.gptr, ctx->g11.glist, ctx->geom, ctx->g12.rowptr, ctx->rowptr, n2, nv,
-            ctx->g11.nnz, A, d_cm, d_cl, ctx->vals, ctx->m11, ctx->l11);
+            ctx->g11.nnz, A, K, ctx->vals, ctx->m11, ctx->l11);
         LAUNCH_CHECK(ctx);
     }
-    CUDA_CHECK(cudaStreamSynchronize(st));   // small coefficient uploads are freed below
-    for (void* p : tmp) cudaFree(p);
     ctx->lhs_ready = true;
 }
 
@@ -412,19 +411,13 @@ void assemble_prec(mpet_ctx* ctx, cudaStream_t st) {
     if (!ctx->lhs_ready) {   // m11 / l11 not yet computed
         k_asm11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(
             ctx->g11.rowptr, ctx->g11.gptr, ctx->g11.glist, ctx->geom, ctx->g12.rowptr, ctx->rowptr, ctx->N2,
-            ctx->Nv, ctx->g11.nnz, A, nullptr, nullptr, nullptr, ctx->m11, ctx->l11);
+            ctx->Nv, ctx->g11.nnz, A, AsmCoefs(), nullptr, ctx->m11, ctx->l11);
         LAUNCH_CHECK(ctx);
     }
     if (!ctx->pp11) ctx->pp11 = dev_alloc<double>(ctx, (int64_t)A * ctx->g11.nnz);
-    const double* cm = ctx->coef.pm;      // mpetsolver.py:270-271 / mpettotalpressuresolver.py:279-282
-    const double* ck = ctx->coef.pk;
-    std::vector<void*> tmp;
-    double* d_cm = upload_small(ctx, cm, A, st, tmp);
-    double* d_ck = upload_small(ctx, ck, A, st, tmp);
-    k_prec11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(ctx->m11, ctx->l11, ctx->g11.nnz, A, d_cm, d_ck,
-                                                          ctx->pp11);
+    AsmCoefs K;                           // mpetsolver.py:270-271 / mpettotalpressuresolver.py:279-282
+    for (int i = 0; i < MPET_MAX_NETWORKS; ++i) { K.cup[i] = ctx->coef.pm[i]; K.cpu[i] = ctx->coef.pk[i]; }
+    k_prec11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(ctx->m11, ctx->l11, ctx->g11.nnz, A, K, ctx->pp11);
     LAUNCH_CHECK(ctx);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    for (void* p : tmp) cudaFree(p);
     ctx->prec_ready = true;
 }

@@ -158,6 +158,7 @@ struct mpet_ctx {
     uint8_t* bc_mask = nullptr;  // [N] 1 on Dirichlet rows (API numbering)
     uint8_t* bc_mask_int = nullptr;   // [Nint] same in the solver-internal layout
     int32_t* bc_dofs_int = nullptr;   // [n_bc] internal indices of the Dirichlet dofs
+    int* d_missing = nullptr;         // mpet_add_entries: count of entries outside the pattern
     double* scratch_int[2] = {nullptr, nullptr};   // [Nint] layout-conversion buffers
     BlockPlan plan_u, plan_p;         // chunk tables of the staged block SpMV
     bool staged_ok = false;

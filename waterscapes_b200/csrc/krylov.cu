@@ -29,9 +29,12 @@ const int kRedThreads = 256;
 
 enum {
     S_BETA = 0, S_BETA_OLD, S_ETA, S_C, S_C_OLD, S_S, S_S_OLD, S_ALPHA, S_RHO1, S_RHO2, S_RHO3, S_CETA,
-    S_NORM, S_NORM0, S_TOL, S_DP, S_COUNT = 32
+    S_NORM, S_NORM0, S_TOL, S_DP, S_BNORM, S_STAG_REF, S_COUNT = 32
 };
-enum { F_DONE = 0, F_CONV, F_ITERS, F_MAXIT, F_BREAKDOWN, F_PENDING, F_COUNT = 8 };
+enum { F_DONE = 0, F_CONV, F_ITERS, F_MAXIT, F_BREAKDOWN, F_PENDING, F_STAG, F_COUNT = 8 };
+// stagnation exit: less than 1 % reduction of the (monotone) MINRES residual norm over kStagWindow iterations
+const int kStagWindow = 256;
+const double kStagFactor = 0.99;
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* sm) {
 #pragma unroll
@@ -77,11 +80,12 @@ k_final_store(const double* __restrict__ partials, int nparts, double* __restric
     if (threadIdx.x == 0) *out = s;
 }
 
-// r = mask ? 0 : b - y
+// r = mask ? (dvals ? dvals : 0) : b - y
 __global__ void k_residual(const double* __restrict__ b, const double* __restrict__ y,
-                           const uint8_t* __restrict__ mask, int64_t n, double* __restrict__ r) {
+                           const uint8_t* __restrict__ mask, int64_t n, double* __restrict__ r,
+                           const double* __restrict__ dvals) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) r[i] = (mask && mask[i]) ? 0.0 : b[i] - y[i];
+    if (i < n) r[i] = (mask && mask[i]) ? (dvals ? dvals[i] : 0.0) : b[i] - y[i];
 }
 
 __global__ void k_jacobi(const double* __restrict__ dinv, const double* __restrict__ r, int64_t n,
@@ -111,7 +115,8 @@ __global__ void __launch_bounds__(kRedThreads)
 k_minres_init(const double* __restrict__ red, double rtol, double atol, int maxit,
               double* __restrict__ sc, int* __restrict__ fl) {
     if (threadIdx.x != 0) return;
-    double dp = *red;
+    const double dp = red[0];       // r0 . B r0
+    const double dpb = red[1];      // b . B b  (b after the symmetric Dirichlet elimination)
     for (int i = 0; i < S_COUNT; ++i) sc[i] = 0.0;
     for (int i = 0; i < F_COUNT; ++i) fl[i] = 0;
     fl[F_MAXIT] = maxit;
@@ -119,7 +124,12 @@ k_minres_init(const double* __restrict__ red, double rtol, double atol, int maxi
     double beta = sqrt(dp);
     sc[S_BETA] = beta; sc[S_ETA] = beta; sc[S_C] = 1.0; sc[S_C_OLD] = 1.0;
     sc[S_NORM] = beta; sc[S_NORM0] = beta;
-    sc[S_TOL] = fmax(rtol * beta, atol);
+    // PETSc's default test (KSPConvergedDefault) with a nonzero initial guess: the reference norm is the
+    // preconditioned norm of the RIGHT-HAND SIDE, not of the initial residual; a zero rhs falls back to |r0|
+    double bnorm = dpb > 0.0 ? sqrt(dpb) : beta;
+    sc[S_BNORM] = bnorm;
+    sc[S_STAG_REF] = 1e300;
+    sc[S_TOL] = fmax(rtol * bnorm, atol);
     if (beta <= sc[S_TOL] || beta == 0.0) { fl[F_CONV] = 1; fl[F_DONE] = 1; }
 }
 
@@ -192,7 +202,11 @@ k_minres_rotate(const double* __restrict__ red, double* __restrict__ sc, int* __
     int it = fl[F_ITERS] + 1;
     fl[F_ITERS] = it;
     if (sc[S_NORM] <= sc[S_TOL]) fl[F_CONV] = 1;
-    if (fl[F_CONV] || it >= fl[F_MAXIT] || beta == 0.0 || fl[F_BREAKDOWN]) fl[F_PENDING] = 1;
+    if (it % kStagWindow == 0) {
+        if (sc[S_NORM] > kStagFactor * sc[S_STAG_REF]) fl[F_STAG] = 1;
+        sc[S_STAG_REF] = sc[S_NORM];
+    }
+    if (fl[F_CONV] || it >= fl[F_MAXIT] || beta == 0.0 || fl[F_BREAKDOWN] || fl[F_STAG]) fl[F_PENDING] = 1;
 }
 
 // w = (u - rho2 w1 - rho3 w2) / rho1 ; x += c*eta*w ; shift Lanczos vectors
@@ -383,9 +397,29 @@ static void initial_residual(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
     dist_halo(ctx, DIST_PLAN_KRYLOV, k->xi, false, nullptr, st);      // ghosts of x and b come from their owners
     dist_halo(ctx, DIST_PLAN_KRYLOV, k->bi, false, nullptr, st);
     block_spmv(ctx, k->xi, k->v, nullptr, nullptr, st);
-    k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr, k->n, k->r);
+    k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr, k->n, k->r,
+                                                    nullptr);
     LAUNCH_CHECK(ctx);
     dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);       // ghost rows of the local matrix are incomplete
+}
+
+// k->r = right-hand side after apply_symmetric(bc, A, b) (bc_symmetric.py:11-22): b - A[:, D] x_D on the free rows,
+// the boundary values on the Dirichlet rows.  PETSc measures convergence against ITS preconditioned norm when the
+// initial guess is nonzero (KSPConvergedDefault [EXT]); bi must be set, k->w1 / k->v are scratch.
+static void eliminated_rhs(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
+    if (ctx->n_bc > 0) {
+        CUDA_CHECK(cudaMemsetAsync(k->w1, 0, sizeof(double) * k->n, st));
+        scatter_bc_values_int(ctx, k->w1, st);
+        dist_halo(ctx, DIST_PLAN_KRYLOV, k->w1, false, nullptr, st);
+        dist_halo(ctx, DIST_PLAN_KRYLOV, k->bi, false, nullptr, st);
+        block_spmv(ctx, k->w1, k->v, nullptr, nullptr, st);
+        k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->bc_mask_int, k->n, k->r, k->w1);
+        LAUNCH_CHECK(ctx);
+    } else {
+        dist_halo(ctx, DIST_PLAN_KRYLOV, k->bi, false, nullptr, st);
+        CUDA_CHECK(cudaMemcpyAsync(k->r, k->bi, sizeof(double) * k->n, cudaMemcpyDeviceToDevice, st));
+    }
+    dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);
 }
 
 static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
@@ -394,6 +428,10 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
     to_internal(ctx, b, k->bi, st);
     to_internal(ctx, x, k->xi, st);
+    eliminated_rhs(ctx, k, st);                              // reference norm sqrt(b . B b) -> red[1]
+    pc_apply_dist(ctx, k->r, k->z, nullptr, st);
+    dot_to(ctx, k, k->r, k->z, nullptr, st);
+    CUDA_CHECK(cudaMemcpyAsync(k->red + 1, k->red, sizeof(double), cudaMemcpyDeviceToDevice, st));
     initial_residual(ctx, k, st);
     pc_apply_dist(ctx, k->r, k->z, nullptr, st);
     dot_to(ctx, k, k->r, k->z, nullptr, st);
@@ -439,9 +477,12 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     prof_collect(ctx);
     info[0] = (double)k->h_fl[F_ITERS];
     info[1] = (double)k->h_fl[F_CONV];
-    info[2] = k->h_sc[S_NORM0] > 0 ? k->h_sc[S_NORM] / k->h_sc[S_NORM0] : 0.0;
+    info[2] = k->h_sc[S_BNORM] > 0 ? k->h_sc[S_NORM] / k->h_sc[S_BNORM] : 0.0;
     info[3] = k->h_sc[S_NORM0];
     info[4] = (double)k->h_fl[F_BREAKDOWN];
+    // KSPConvergedReason-style code: 2 rtol/atol reached, -3 iteration limit, -4 breakdown, -5 stagnation
+    info[5] = k->h_fl[F_CONV] ? 2.0 : (k->h_fl[F_BREAKDOWN] ? -4.0 : (k->h_fl[F_STAG] ? -5.0 : -3.0));
+    info[6] = k->h_sc[S_BNORM];
 }
 
 // ---------------------------------------------------------------------------------- GMRES(m)
@@ -482,7 +523,15 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
     int iters = 0;
     bool converged = false;
-    double norm0 = -1, norm = 0, tol = 0;
+    double norm0 = -1, norm = 0, tol = 0, bnorm = 0;
+    {   // PETSc default with a nonzero initial guess: tolerance relative to ||B b||_2 (left preconditioning)
+        eliminated_rhs(ctx, k, st);
+        pc_apply_dist(ctx, k->r, k->z, nullptr, st);
+        dot_to(ctx, k, k->z, k->z, nullptr, st);
+        CUDA_CHECK(cudaMemcpyAsync(&bnorm, k->red, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        bnorm = std::sqrt(bnorm);
+    }
     while (!converged && iters < ctx->maxit) {
         initial_residual(ctx, k, st);
         pc_apply_dist(ctx, k->r, k->z, nullptr, st);
@@ -491,7 +540,11 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         CUDA_CHECK(cudaMemcpyAsync(&bb, k->red, sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         double beta = std::sqrt(bb);
-        if (norm0 < 0) { norm0 = beta; tol = std::max(ctx->rtol * norm0, ctx->atol); }
+        if (norm0 < 0) {
+            norm0 = beta;
+            if (!(bnorm > 0.0)) bnorm = beta;
+            tol = std::max(ctx->rtol * bnorm, ctx->atol);
+        }
         norm = beta;
         if (beta <= tol || beta == 0.0) { converged = true; break; }
         k_scale_copy<<<grid_for(n, 256), 256, 0, st>>>(k->z, 1.0 / beta, n, V);
@@ -559,9 +612,11 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     CUDA_CHECK(cudaStreamSynchronize(st));
     info[0] = iters;
     info[1] = converged ? 1.0 : 0.0;
-    info[2] = norm0 > 0 ? norm / norm0 : 0.0;
+    info[2] = bnorm > 0 ? norm / bnorm : 0.0;
     info[3] = norm0 < 0 ? 0.0 : norm0;
     info[4] = 0.0;
+    info[5] = converged ? 2.0 : -3.0;
+    info[6] = bnorm;
 }
 
 void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {

@@ -15,13 +15,16 @@
 
 namespace {
 
+struct PrevCoefs { double c[2 * MPET_MAX_NETWORKS + MPET_MAX_NETWORKS * MPET_MAX_NETWORKS]; };
+
 __global__ void __launch_bounds__(256)
 k_rhs_prev(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
            const double* __restrict__ vals, const int32_t* __restrict__ rp12,
            const int32_t* __restrict__ rp11, const int32_t* __restrict__ col11,
            const double* __restrict__ m11, const double* __restrict__ l11, int64_t n2, int64_t nv, int A,
-           const double* __restrict__ coef /* [A] ru, [A] rl, [A*A] rm */,
+           const PrevCoefs K /* by value: no per-step allocation */,
            const double* __restrict__ up, double* __restrict__ b) {
+    const double* coef = K.c;       // [A] ru, [A] rl, [A*A] rm
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (w >= (int64_t)A * nv) return;
@@ -134,22 +137,17 @@ void rhs_prev(mpet_ctx* ctx, const double* up, double* b, cudaStream_t st) {
     const int A = ctx->A;
     CUDA_CHECK(cudaMemsetAsync(b, 0, sizeof(double) * 3 * ctx->N2, st));
     if (A == 0) return;
-    double coef[2 * MPET_MAX_NETWORKS + MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
+    PrevCoefs K;
+    double* coef = K.c;
     for (int i = 0; i < A; ++i) {
         coef[i] = ctx->coef.ru[i];
         coef[A + i] = ctx->coef.rl[i];
         for (int j = 0; j < A; ++j) coef[2 * A + i * A + j] = ctx->coef.rm[i * A + j];
     }
-    double* d_coef = nullptr;
-    int n = 2 * A + A * A;
-    CUDA_CHECK(cudaMalloc(&d_coef, sizeof(double) * n));
-    CUDA_CHECK(cudaMemcpyAsync(d_coef, coef, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     k_rhs_prev<<<grid_for((int64_t)A * ctx->Nv * 32, 256), 256, 0, st>>>(
         ctx->rowptr, ctx->cols, ctx->vals, ctx->g12.rowptr, ctx->g11.rowptr, ctx->g11.col, ctx->m11,
-        ctx->l11, ctx->N2, ctx->Nv, A, d_coef, up, b);
+        ctx->l11, ctx->N2, ctx->Nv, A, K, up, b);
     LAUNCH_CHECK(ctx);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(d_coef);
 }
 
 void export_values(mpet_ctx* ctx, int which, double* out, cudaStream_t st) {
@@ -206,14 +204,13 @@ void add_entries(mpet_ctx* ctx, const int32_t* r, const int32_t* c, const double
                  cudaStream_t st) {
     MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run before mpet_add_entries");
     if (n == 0) return;
-    int* d_missing = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_missing, sizeof(int)));
+    if (!ctx->d_missing) ctx->d_missing = dev_alloc<int>(ctx, 1);
+    int* d_missing = ctx->d_missing;
     CUDA_CHECK(cudaMemsetAsync(d_missing, 0, sizeof(int), st));
     k_add_entries<<<grid_for(n, 256), 256, 0, st>>>(ctx->rowptr, ctx->cols, r, c, v, n, ctx->vals, d_missing);
     LAUNCH_CHECK(ctx);
     int missing = 0;
     CUDA_CHECK(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(d_missing);
     MPET_REQUIRE(missing == 0, "mpet_add_entries: entry outside the sparsity pattern");
 }

@@ -159,7 +159,8 @@ class Engine:
     def solve(self, b, x):
         info = (C.c_double * 8)()
         self._ck(self.lib.mpet_solve(self._ctx, _ptr(b), _ptr(x), info, self._stream()))
-        return dict(niter=int(info[0]), converged=bool(info[1]), rel_res=float(info[2]), res0=float(info[3]))
+        return dict(niter=int(info[0]), converged=bool(info[1]), rel_res=float(info[2]), res0=float(info[3]),
+                    breakdown=bool(info[4]), reason=int(info[5]), bnorm=float(info[6]))
 
     def pc_apply(self, r, z):
         self._ck(self.lib.mpet_pc_apply(self._ctx, _ptr(r), _ptr(z), self._stream()))

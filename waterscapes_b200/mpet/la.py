@@ -210,7 +210,7 @@ class PETScKrylovSolver:
         self.pc = {"hypre_amg": "amg", "amg": "amg", "jacobi": "jacobi", "none": "none"}[preconditioner]
         self.parameters = {"relative_tolerance": 1e-5, "absolute_tolerance": 1e-50,
                            "maximum_iterations": 10000, "nonzero_initial_guess": False,
-                           "gmres_restart": 30}
+                           "gmres_restart": 30, "error_on_nonconvergence": True}
         self.A = self.P = None
         self.last_info = None
 
@@ -235,8 +235,14 @@ class PETScKrylovSolver:
         bt = b.t if isinstance(b, Vector) else b
         if not p["nonzero_initial_guess"]:
             xt.zero_()
-        self.last_info = eng.solve(bt, xt)
-        return self.last_info["niter"]
+        self.last_info = info = eng.solve(bt, xt)
+        if not info["converged"] and p["error_on_nonconvergence"]:
+            # DOLFIN's default (error_on_nonconvergence=True): a failed Krylov solve must not be stepped over
+            why = {-3: "iteration limit reached", -4: "breakdown (indefinite preconditioner)",
+                   -5: "stagnation"}.get(info["reason"], "reason %d" % info["reason"])
+            raise RuntimeError("Krylov solve (%s) did not converge after %d iterations: %s; ||r||/||b|| = %.3e"
+                               % (self.method, info["niter"], why, info["rel_res"]))
+        return info["niter"]
 
 
 class LUSolver:

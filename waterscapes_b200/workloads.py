@@ -51,8 +51,12 @@ def make_problem(name, n=None, mesh=None):
                                     "0.1*sin(pi*x[0])*sin(pi*x[1])*cos(pi*x[2])*sin(pi*t)"), t=time, degree=2)
         problem.p_bar = [Expression("%d*sin(pi*x[0])*cos(pi*x[1])*sin(pi*x[2])*sin(2*pi*t)" % (i + 1), t=time,
                                     degree=1) for i in range(2)]
-        problem.f = Expression(("sin(pi*x[0])*sin(pi*t)", "cos(pi*x[1])*sin(pi*t)", "x[2]*sin(pi*t)"), t=time, degree=2)
-        problem.g = [Expression("%d*cos(pi*x[0])*cos(2*pi*t)" % (i + 1), t=time, degree=1) for i in range(2)]
+        # f, g derived with sympy from the exact (u, p) above so that cfg1 doubles as a convergence check
+        from .mms import cfg1_exact, standard_sources
+        mms = standard_sources(params, *cfg1_exact())
+        problem.f = Expression(lambda x, t: mms["f"](x, t), t=time, degree=2)
+        problem.g = [Expression(lambda x, t, i=i: mms["g"][i](x, t), t=time, degree=1) for i in range(2)]
+        problem.mms = mms
         on_boundary.mark(problem.momentum_boundary_markers, 0)
         for i in range(2):
             on_boundary.mark(problem.continuity_boundary_markers[i], 0)
