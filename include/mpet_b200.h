@@ -129,9 +129,14 @@ int mpet_csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr_dev, const
  * the initial residual); MINRES also stops when the residual norm fell by < 1 % over 256 iterations
  * (stagnation at round-off).  Synchronous.  info_host f64[8]: [0] iterations, [1] converged flag,
  * [2] final ||r||_B / ||b||_B, [3] initial residual norm, [4] breakdown flag (indefinite preconditioner),
- * [5] reason (2 tolerance reached, -3 iteration limit, -4 breakdown, -5 stagnation), [6] ||b||_B. */
+ * [5] reason (2 tolerance reached, -3 iteration limit, -4 breakdown, -5 stagnation), [6] the reference norm of the
+ * test (mpet_krylov_reference_norm), [7] ||b||_B. */
 int mpet_krylov_setup(mpet_ctx* ctx, int method, int pc, double rtol, double atol, int maxit,
                       int restart);
+/* reference norm of the convergence test: 0 = ||b||_B (PETSc default, KSPConvergedDefault), 1 = min(||b||_B,
+ * ||r0||_B) (KSPConvergedDefaultSetUMIRNorm) -- used by the LUSolver stand-in, whose answer must not depend on how
+ * large the boundary data is compared with the update of one time step */
+int mpet_krylov_reference_norm(mpet_ctx* ctx, int mode);
 int mpet_pc_setup(mpet_ctx* ctx, void* stream);
 int mpet_solve(mpet_ctx* ctx, const double* b_dev, double* x_dev, double* info_host, void* stream);
 /* apply the preconditioner once: z = M^-1 r (tests) */
@@ -168,6 +173,11 @@ int64_t mpet_launch_count(mpet_ctx* ctx, int reset);
  * [8..15] launch-group counts.  Synchronises the device. */
 int mpet_profile(mpet_ctx* ctx, int enable, double* out_host);
 int64_t mpet_device_bytes(mpet_ctx* ctx);
+/* algorithmic bytes of the last preconditioner application (sum over all levels and passes: matrix stream,
+ * gathered vector entries and row-wise operands once each); bench.py's second roofline entry */
+int64_t mpet_pc_bytes(mpet_ctx* ctx);
+/* how ghost entries travel: 0 single GPU, 1 NCCL send/recv + all-reduce, 2 peer-memory kernels over NVLink */
+int mpet_comm_kind(mpet_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -2,7 +2,8 @@
 (src/mpet/test/test_convergence_mpetsolver.py:103-245, test_convergence_totalpressuresolver.py:103-253), run
 through MPETSolver / MPETTotalPressureSolver exactly as the reference tests drive their solvers (same material
 parameters, same boundary split -- Neumann traction sigma.n on x = 1, Dirichlet elsewhere --, same time grids),
-with the reference's rate thresholds (:234-239 and :237-242) asserted on the finest pair of UnitCubeMesh(4, 8, 16).
+with the reference's rate thresholds (:234-239 and :237-242) asserted on the finest pair of the reference's own
+mesh sequence n = 8, 16, 32 (the pair 8 -> 16 is still pre-asymptotic in 3-D: pressure L2 rates 1.6-1.7).
 Nothing here touches oracle/: exact solutions and error norms come from tests/mms3d.py."""
 import numpy as np
 import pytest
@@ -65,7 +66,7 @@ def _single_run(n, M, theta, total_pressure):
 
 
 @pytest.mark.parametrize("solver_kind", ["standard", "total_pressure"])
-@pytest.mark.parametrize("theta,ns,ms", [(0.5, [4, 8, 16], [4, 8, 16]), (1.0, [4, 8, 16], [8, 32, 128])])
+@pytest.mark.parametrize("theta,ns,ms", [(0.5, [8, 16, 32], [4, 8, 16]), (1.0, [8, 16, 32], [8, 32, 128])])
 def test_mms_convergence_rates_3d(solver_kind, theta, ns, ms):
     tp = solver_kind == "total_pressure"
     res = [_single_run(n, m, theta, tp) for n, m in zip(ns, ms)]

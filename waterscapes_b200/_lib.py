@@ -43,6 +43,7 @@ PROTOTYPES = {
     "mpet_spmv": (_int, [_c_ctx, _p, _p, _p]),
     "mpet_csr_spmv": (_int, [_c_ctx, _i64, _p, _p, _p, _p, _p, _f64, _p]),
     "mpet_krylov_setup": (_int, [_c_ctx, _int, _int, _f64, _f64, _int, _int]),
+    "mpet_krylov_reference_norm": (_int, [_c_ctx, _int]),
     "mpet_pc_setup": (_int, [_c_ctx, _p]),
     "mpet_solve": (_int, [_c_ctx, _p, _p, C.POINTER(_f64), _p]),
     "mpet_pc_apply": (_int, [_c_ctx, _p, _p, _p]),
@@ -52,6 +53,8 @@ PROTOTYPES = {
     "mpet_launch_count": (_i64, [_c_ctx, _int]),
     "mpet_profile": (_int, [_c_ctx, _int, C.POINTER(_f64)]),
     "mpet_device_bytes": (_i64, [_c_ctx]),
+    "mpet_pc_bytes": (_i64, [_c_ctx]),
+    "mpet_comm_kind": (_int, [_c_ctx]),
 }
 
 _lib = None

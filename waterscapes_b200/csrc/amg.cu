@@ -578,9 +578,17 @@ const double kChebRatio = 4.0;    // smooth the upper [lambda_max / ratio, lambd
 const int64_t kCoarseMax = 300;
 const int kMaxLevels = 12;
 
+// Algorithmic bytes of one pass (bench.py's preconditioner roofline): the matrix stream once (8-byte value +
+// 4-byte column index per entry, row pointers), every gathered vector entry once, the row-wise operands once.
+inline int64_t spmm_bytes(const DevCsr& M, int W, int row_streams) {
+    return 12 * M.nnz + 4 * (M.nrows + 1) + 8 * (int64_t)W * M.ncols + 8 * (int64_t)W * M.nrows * row_streams;
+}
+
 template <int W, int EPI>
 void launch_epi(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const double* x, const double* b, double* out,
                 double* d, const double* dinv, double c1, double c2, const int* done, cudaStream_t st) {
+    // RESID: read b, write out.  CHEB: read b, (d), dinv; write d, out
+    ctx->pc_bytes_acc += EPI == EPI_RESID ? spmm_bytes(M, W, 2) : spmm_bytes(M, W, 3 + (c1 != 0.0)) + 8 * M.nrows;
     if (plan.nchunks > 0) {
         staged_spmm(ctx, W, EPI, plan, M, x, b, out, d, dinv, c1, c2, done, st);
         return;
@@ -599,6 +607,7 @@ void launch_epi(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const doub
 template <int W>
 void launch_plain(mpet_ctx* ctx, const DevCsr& M, const SpmmPlan& plan, const double* x, double* y, double beta,
                   const int* done, cudaStream_t st) {
+    ctx->pc_bytes_acc += spmm_bytes(M, W, 1 + (beta != 0.0));
     if (plan.nchunks > 0) {
         staged_spmm(ctx, W, 2, plan, M, x, nullptr, y, nullptr, nullptr, beta, 0.0, done, st);
         return;
@@ -646,6 +655,7 @@ void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, 
             if (cur == nullptr) {
                 k_cheb_first<W><<<grid_for(n * W, 256), 256, 0, st>>>(n, b, L.dinv, 1.0 / theta, L.r, dst, done);
                 LAUNCH_CHECK(ctx);
+                ctx->pc_bytes_acc += 8 * n * (3 * W + 1);
             } else {
                 launch_epi<W, EPI_CHEB>(ctx, L.A, L.planA, cur, b, dst, L.r, L.dinv, 0.0, 1.0 / theta, done, st);
             }
@@ -677,6 +687,7 @@ void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x,
         if (H.coarse_inv) {
             k_dense_apply<W><<<grid_for((int64_t)n * 32, 256), 256, 0, st>>>((int)n, H.coarse_inv, b, x, done);
             LAUNCH_CHECK(ctx);
+            ctx->pc_bytes_acc += 8 * n * n + 16 * n * W;
         } else {
             chebyshev<W>(ctx, L, b, nullptr, x, done, st);
         }
@@ -690,7 +701,7 @@ void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x,
     if (lev == H.transition) {
         // restrict onto this rank's aggregates, all-gather the padded slots: coarser levels are replicated
         launch_plain<W>(ctx, C.R, C.planR, L.t, H.gather_send, 0.0, done, st);
-        dist_allgather(ctx, H.gather_send, C.b, H.gather_count * W, st);
+        dist_allgather(ctx, H.gather_send, C.b, H.gather_count * W, done, st);
     } else {
         launch_plain<W>(ctx, C.R, C.planR, L.t, C.b, 0.0, done, st);                           // restrict
         if (C.halo_plan >= 0) dist_halo(ctx, C.halo_plan, C.b, false, done, st);
@@ -1010,6 +1021,7 @@ HostCsr distributed_transition(mpet_ctx* ctx, AmgHierarchy& H, int W, cudaStream
     compute_dinv_host(ctx, L, Ac);
     H.levels.push_back(L);
     H.gather_send = dev_alloc<double>(ctx, maxcount * W);
+    dist_reserve_gather(ctx, maxcount * W * nr, st);      // collective: same size on every rank
     return Ac;
 }
 
@@ -1136,6 +1148,7 @@ void amg_free(mpet_ctx* ctx) {
 void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
     MPET_REQUIRE(ctx->prec_ready, "mpet_assemble_prec must run before mpet_pc_setup");
     amg_free(ctx);                    // a new dt / new Dirichlet set rebuilds the hierarchies
+    ctx->graph_epoch++;               // captured iterations hold pointers into the old hierarchies
     struct ArenaGuard {
         mpet_ctx* c;
         explicit ArenaGuard(mpet_ctx* c_) : c(c_) { c->arena = &c->amg_allocs; }
@@ -1233,6 +1246,7 @@ static void cycles(mpet_ctx* ctx, AmgHierarchy& H, int ncycles, const double* b,
         vcycle<W>(ctx, H, 0, H.cyc_r, H.cyc_e, done, st);
         k_add_inplace<<<grid_for(L.A.nrows * W, 256), 256, 0, st>>>(L.A.nrows * W, H.cyc_e, x, done);
         LAUNCH_CHECK(ctx);
+        ctx->pc_bytes_acc += 24 * L.A.nrows * W;
     }
 }
 
@@ -1240,7 +1254,15 @@ static void cycles(mpet_ctx* ctx, AmgHierarchy& H, int ncycles, const double* b,
 // cycles; on one GPU the per-field cycles (dozens of small launches each) run on their own high-priority
 // streams beside the displacement cycle and join before returning.  Multi-GPU keeps one stream: the halo
 // exchanges of all cycles share one NCCL communicator and must be issued in one order on every rank.
+static void amg_apply_impl(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st);
+
 void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
+    ctx->pc_bytes_acc = 0;
+    amg_apply_impl(ctx, r, z, done, st);
+    ctx->pc_bytes_last = ctx->pc_bytes_acc;
+}
+
+static void amg_apply_impl(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaStream_t st) {
     const int64_t n2 = ctx->N2, nv = ctx->Nv;
     static const bool want_streams = []() { const char* e = getenv("MPET_PC_STREAMS"); return !(e && e[0] == '0'); }();
     static const int p_cycles = []() { const char* e = getenv("MPET_P_CYCLES"); return e ? std::max(1, atoi(e)) : 0; }();
@@ -1296,12 +1318,17 @@ void amg_apply(mpet_ctx* ctx, const double* r, double* z, const int* done, cudaS
         CUDA_CHECK(cudaStreamWaitEvent(st, ctx->pc_join[0], 0));
         return;
     }
+    // serial order (MPET_PC_STREAMS=0): also the measurement mode of the per-block times (mpet_profile 6, 7)
+    cudaEvent_t pe = prof_begin(ctx, st);
     cycles<4>(ctx, *ctx->amg_u, u_cycles, r, z, done, st);
+    prof_end(ctx, PROF_PC_U, pe, st);
+    pe = prof_begin(ctx, st);
     for (int i = 0; i < ctx->A; ++i) {
         const int64_t off = 4 * n2 + (int64_t)i * nv;
         AmgHierarchy& H = *ctx->amg_p[i];
         cycles<1>(ctx, H, H.poly_degree ? 1 : p_cyc, r + off, z + off, done, st);
     }
+    prof_end(ctx, PROF_PC_P, pe, st);
 }
 
 int amg_num_levels(mpet_ctx* ctx, int block) {

@@ -53,7 +53,7 @@ static cudaEvent_t prof_event(mpet_ctx* ctx) {
 }
 
 cudaEvent_t prof_begin(mpet_ctx* ctx, cudaStream_t st) {
-    if (!ctx->prof.on || ctx->prof.pending.size() > 20000) return nullptr;
+    if (!ctx->prof.on || ctx->prof_suspended || ctx->prof.pending.size() > 20000) return nullptr;
     cudaEvent_t a = prof_event(ctx);
     CUDA_CHECK(cudaEventRecord(a, st));
     return a;
@@ -124,6 +124,7 @@ void mpet_destroy(mpet_ctx* ctx) {
         dist_free(ctx);
         for (int i = 0; i < ctx->pc_streams_ready; ++i) { cudaStreamDestroy(ctx->pc_stream[i]); cudaEventDestroy(ctx->pc_join[i]); }
         if (ctx->pc_fork) cudaEventDestroy(ctx->pc_fork);
+        if (ctx->solve_stream) { cudaStreamDestroy(ctx->solve_stream); cudaEventDestroy(ctx->solve_event); }
         for (void* p : ctx->allocs) cudaFree(p);
     } catch (...) {
     }
@@ -396,6 +397,13 @@ int mpet_krylov_setup(mpet_ctx* ctx, int method, int pc, double rtol, double ato
     MPET_CATCH(ctx)
 }
 
+int mpet_krylov_reference_norm(mpet_ctx* ctx, int mode) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(mode == 0 || mode == 1, "mode: 0 = |b| (PETSc default), 1 = min(|b|, |r0|)");
+    ctx->norm_mode = mode;
+    MPET_CATCH(ctx)
+}
+
 int mpet_pc_setup(mpet_ctx* ctx, void* stream) {
     MPET_TRY(ctx)
     pc_setup(ctx, as_stream(stream));
@@ -445,5 +453,9 @@ int64_t mpet_launch_count(mpet_ctx* ctx, int reset) {
 }
 
 int64_t mpet_device_bytes(mpet_ctx* ctx) { return ctx->bytes; }
+
+int64_t mpet_pc_bytes(mpet_ctx* ctx) { return ctx->pc_bytes_last; }
+
+int mpet_comm_kind(mpet_ctx* ctx) { return dist_comm_kind(ctx); }
 
 }  // extern "C"

@@ -85,7 +85,7 @@ struct AmgHierarchy {
 };
 
 // CUDA-event profiler: per-category device time of the launches made inside the library
-enum { PROF_SPMV = 0, PROF_PC = 1, PROF_VEC = 2, PROF_ASM = 3, PROF_RHS = 4, PROF_COMM = 5, PROF_NCAT = 8 };
+enum { PROF_SPMV = 0, PROF_PC = 1, PROF_VEC = 2, PROF_ASM = 3, PROF_RHS = 4, PROF_COMM = 5, PROF_PC_U = 6, PROF_PC_P = 7, PROF_NCAT = 8 };
 struct Prof {
     bool on = false;
     struct Span { int cat; cudaEvent_t a, b; };
@@ -116,6 +116,8 @@ struct mpet_ctx {
     std::string err;
     int64_t launches = 0;
     int64_t bytes = 0;
+    int64_t pc_bytes_acc = 0;     // algorithmic bytes of the preconditioner application in flight (amg.cu)
+    int64_t pc_bytes_last = 0;    // ... of the last complete application (mpet_pc_bytes)
     std::vector<void*> allocs;
     std::vector<void*> amg_allocs;          // freed and rebuilt by every mpet_pc_setup
     std::vector<void*>* arena = nullptr;    // when set, dev_alloc records here instead of allocs
@@ -166,6 +168,7 @@ struct mpet_ctx {
     // Krylov
     int method = 0, pc = 2, maxit = 10000, restart = 30;
     double rtol = 1e-5, atol = 1e-50;
+    int norm_mode = 0;           // reference norm of the convergence test: 0 = |b|_B (PETSc default), 1 = min(|b|_B, |r0|_B)
     struct KrylovWork* kw = nullptr;
     struct DistState* dist = nullptr;           // NCCL communicator + halo plan (dist.cu)
     AmgHierarchy* amg_u = nullptr;              // scalar P2 block, 3 right-hand sides
@@ -175,7 +178,11 @@ struct mpet_ctx {
     cudaStream_t pc_stream[MPET_MAX_NETWORKS] = {};
     cudaEvent_t pc_fork = nullptr, pc_join[MPET_MAX_NETWORKS] = {};
     int pc_streams_ready = 0;
-    int dist_lane = 0;           // which NCCL communicator / staging buffers dist_halo and dist_allgather use (dist.cu)
+    cudaStream_t solve_stream = nullptr;     // used when the caller hands us the (uncapturable) legacy default stream
+    cudaEvent_t solve_event = nullptr;
+    int dist_lane = 0;           // which lane (flags + staging areas / communicator) dist_halo and dist_allgather use (dist.cu)
+    bool prof_suspended = false; // inside a stream capture: no profiler events
+    int64_t graph_epoch = 0;     // bumped whenever pointers baked into captured launches change (graphs are re-captured)
 };
 
 // ---- helpers --------------------------------------------------------------------------------
@@ -242,6 +249,7 @@ void staged_spmm(mpet_ctx* ctx, int W, int epi, const SpmmPlan& P, const DevCsr&
 // P1WA: the A vertex fields of the merged pressure hierarchy (entry i*Nv + v)
 enum { DIST_PLAN_KRYLOV = 0, DIST_PLAN_P2W4 = 1, DIST_PLAN_P1W4 = 2, DIST_PLAN_P1W1 = 3, DIST_PLAN_P1WA = 4, DIST_NPLANS = 5 };
 bool dist_active(mpet_ctx* ctx);
+int dist_comm_kind(mpet_ctx* ctx);      // 0: single GPU, 1: NCCL send/recv + all-reduce, 2: peer-memory kernels over NVLink
 bool dist_has_lane1(mpet_ctx* ctx);
 int dist_rank(mpet_ctx* ctx);
 int dist_nranks(mpet_ctx* ctx);
@@ -250,7 +258,11 @@ const std::vector<uint8_t>& dist_own_nodes(mpet_ctx* ctx);
 void dist_halo(mpet_ctx* ctx, int plan, double* v, bool reverse, const int* done, cudaStream_t st);
 void dist_allreduce_sum(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
 void dist_allreduce_max(mpet_ctx* ctx, double* dev_scalars, int count, cudaStream_t st);
-void dist_allgather(mpet_ctx* ctx, const double* send, double* recv, int64_t count, cudaStream_t st);
+void dist_allgather(mpet_ctx* ctx, const double* send, double* recv, int64_t count, const int* done, cudaStream_t st);
+void dist_reserve_gather(mpet_ctx* ctx, int64_t doubles, cudaStream_t st);
+bool dist_reduce_partials(mpet_ctx* ctx, const double* partials, int nparts, int count, double* out, const int* done,
+                          cudaStream_t st);
+void dist_check(mpet_ctx* ctx);
 void dist_bcast_bytes(mpet_ctx* ctx, void* buf, int64_t nbytes, int root, cudaStream_t st);
 // spmv.cu
 void csr_spmv(mpet_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* cols,

@@ -29,7 +29,7 @@ const int kRedThreads = 256;
 
 enum {
     S_BETA = 0, S_BETA_OLD, S_ETA, S_C, S_C_OLD, S_S, S_S_OLD, S_ALPHA, S_RHO1, S_RHO2, S_RHO3, S_CETA,
-    S_NORM, S_NORM0, S_TOL, S_DP, S_BNORM, S_STAG_REF, S_COUNT = 32
+    S_NORM, S_NORM0, S_TOL, S_DP, S_BNORM, S_STAG_REF, S_BTRUE, S_COUNT = 32
 };
 enum { F_DONE = 0, F_CONV, F_ITERS, F_MAXIT, F_BREAKDOWN, F_PENDING, F_STAG, F_COUNT = 8 };
 // stagnation exit: less than 1 % reduction of the (monotone) MINRES residual norm over kStagWindow iterations
@@ -112,7 +112,7 @@ __global__ void k_abs_diag_inv(int64_t n, const int64_t* __restrict__ rowptr, co
 
 // ---------------------------------------------------------------------------------- MINRES
 __global__ void __launch_bounds__(kRedThreads)
-k_minres_init(const double* __restrict__ red, double rtol, double atol, int maxit,
+k_minres_init(const double* __restrict__ red, double rtol, double atol, int maxit, int norm_mode,
               double* __restrict__ sc, int* __restrict__ fl) {
     if (threadIdx.x != 0) return;
     const double dp = red[0];       // r0 . B r0
@@ -127,6 +127,8 @@ k_minres_init(const double* __restrict__ red, double rtol, double atol, int maxi
     // PETSc's default test (KSPConvergedDefault) with a nonzero initial guess: the reference norm is the
     // preconditioned norm of the RIGHT-HAND SIDE, not of the initial residual; a zero rhs falls back to |r0|
     double bnorm = dpb > 0.0 ? sqrt(dpb) : beta;
+    sc[S_BTRUE] = bnorm;
+    if (norm_mode == 1) bnorm = fmin(bnorm, beta);    // KSPConvergedDefaultSetUMIRNorm: min(|b|, |r0|)
     sc[S_BNORM] = bnorm;
     sc[S_STAG_REF] = 1e300;
     sc[S_TOL] = fmax(rtol * bnorm, atol);
@@ -289,6 +291,11 @@ struct KrylovWork {
     double* hdev = nullptr;
     double* h_sc = nullptr;    // pinned mirrors
     int* h_fl = nullptr;
+    // CUDA graphs of the MINRES iteration body: [0..3] its four segments (SpMV | halo + dot | preconditioner |
+    // vector updates), launched one by one when the profiler brackets them with events, [4] the whole iteration
+    cudaGraphExec_t graph[5] = {};
+    int64_t graph_launches[5] = {};
+    int64_t graph_key = -1;
 };
 
 static KrylovWork* get_work(mpet_ctx* ctx) {
@@ -309,8 +316,15 @@ static KrylovWork* get_work(mpet_ctx* ctx) {
     return k;
 }
 
+static void drop_graphs(KrylovWork* k) {
+    for (auto& g : k->graph)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    k->graph_key = -1;
+}
+
 void krylov_free(mpet_ctx* ctx) {
     if (!ctx->kw) return;
+    drop_graphs(ctx->kw);
     cudaFreeHost(ctx->kw->h_sc);
     cudaFreeHost(ctx->kw->h_fl);
     delete ctx->kw;
@@ -377,6 +391,7 @@ void spmv_api(mpet_ctx* ctx, const double* x, double* y, cudaStream_t st) {
 
 // partials -> k->red[0] (fixed order), then the NCCL all-reduce over ranks when a communicator is attached
 static void finish_reduction(mpet_ctx* ctx, KrylovWork* k, const int* done, cudaStream_t st) {
+    if (dist_reduce_partials(ctx, k->partials, kRedBlocks, 1, k->red, done, st)) return;   // one fused launch
     k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->red, done);
     LAUNCH_CHECK(ctx);
     dist_allreduce_sum(ctx, k->red, 1, st);
@@ -435,7 +450,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     initial_residual(ctx, k, st);
     pc_apply_dist(ctx, k->r, k->z, nullptr, st);
     dot_to(ctx, k, k->r, k->z, nullptr, st);
-    k_minres_init<<<1, 32, 0, st>>>(k->red, ctx->rtol, ctx->atol, ctx->maxit, k->sc, k->fl);
+    k_minres_init<<<1, 32, 0, st>>>(k->red, ctx->rtol, ctx->atol, ctx->maxit, ctx->norm_mode, k->sc, k->fl);
     LAUNCH_CHECK(ctx);
     const int* done = k->fl + F_DONE;
     k_minres_start<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->r, k->z, k->v, k->u, k->v_old, k->u_old, k->w1,
@@ -443,29 +458,84 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     LAUNCH_CHECK(ctx);
     const int check_every = 5;
     int enq = 0;
+    // the four segments of one iteration (fixed pointers, scalars on the device: every iteration enqueues the same work)
+    auto seg = [&](int which) {
+        switch (which) {
+            case 0:
+                block_spmv(ctx, k->u, k->r, mask, done, st);
+                break;
+            case 1:
+                dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, done, st);
+                dot_to(ctx, k, k->r, k->u, done, st);
+                k_minres_alpha<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
+                LAUNCH_CHECK(ctx);
+                break;
+            case 2:
+                pc_apply_dist(ctx, k->r, k->z, done, st);
+                break;
+            default:
+                k_minres_update<<<kRedBlocks, kRedThreads, 0, st>>>(n, k->sc, k->v, k->v_old, k->u, k->u_old, k->r,
+                                                                    k->z, k->partials, dist_owned_mask(ctx), done);
+                LAUNCH_CHECK(ctx);
+                finish_reduction(ctx, k, done, st);
+                k_minres_rotate<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
+                LAUNCH_CHECK(ctx);
+                k_minres_finalize<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->xi, k->w1, k->w2, k->v, k->v_old, k->u,
+                                                                    k->u_old, k->r, k->z, done);
+                LAUNCH_CHECK(ctx);
+                k_commit<<<1, 1, 0, st>>>(k->fl);
+                LAUNCH_CHECK(ctx);
+                break;
+        }
+    };
+    // Graph capture: ~160 launches per iteration collapse into 1 (or 4, when the profiler times SpMV and the
+    // preconditioner) graph launches.  The first iteration of every solve runs eagerly (lazy one-time kernel
+    // attributes, side streams); graphs are re-captured when anything baked into the launches changed
+    // (hierarchy, Dirichlet set, peer arena: ctx->graph_epoch).  NCCL halos are not captured.
+    static const bool want_graphs = []() { const char* e = getenv("MPET_GRAPHS"); return !(e && e[0] == '0'); }();
+    const bool can_graph = want_graphs && (!dist_active(ctx) || dist_comm_kind(ctx) == 2);
+    const int64_t key = ctx->graph_epoch * 8 + ctx->pc;
+    if (k->graph_key != key) drop_graphs(k);
+    auto capture = [&](int slot) {
+        ctx->prof_suspended = true;
+        const int64_t l0 = ctx->launches;
+        CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        try {
+            if (slot < 4) seg(slot);
+            else for (int w = 0; w < 4; ++w) seg(w);
+        } catch (...) {
+            cudaGraph_t junk = nullptr;
+            cudaStreamEndCapture(st, &junk);
+            if (junk) cudaGraphDestroy(junk);
+            ctx->prof_suspended = false;
+            throw;
+        }
+        cudaGraph_t g = nullptr;
+        CUDA_CHECK(cudaStreamEndCapture(st, &g));
+        ctx->prof_suspended = false;
+        k->graph_launches[slot] = ctx->launches - l0;
+        ctx->launches = l0;
+        CUDA_CHECK(cudaGraphInstantiate(&k->graph[slot], g, 0));
+        cudaGraphDestroy(g);
+        k->graph_key = key;
+    };
+    auto run = [&](int slot) {
+        if (!k->graph[slot]) capture(slot);
+        CUDA_CHECK(cudaGraphLaunch(k->graph[slot], st));
+        ctx->launches += k->graph_launches[slot];
+    };
     while (true) {
         for (int q = 0; q < check_every && enq < ctx->maxit; ++q, ++enq) {
+            const bool eager = !can_graph || enq == 0;
+            if (!eager && !ctx->prof.on) { run(4); continue; }
             cudaEvent_t pe = prof_begin(ctx, st);
-            block_spmv(ctx, k->u, k->r, mask, done, st);
+            if (eager) seg(0); else run(0);
             prof_end(ctx, PROF_SPMV, pe, st);
-            dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, done, st);
-            dot_to(ctx, k, k->r, k->u, done, st);
-            k_minres_alpha<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
-            LAUNCH_CHECK(ctx);
+            if (eager) seg(1); else run(1);
             pe = prof_begin(ctx, st);
-            pc_apply_dist(ctx, k->r, k->z, done, st);
+            if (eager) seg(2); else run(2);
             prof_end(ctx, PROF_PC, pe, st);
-            k_minres_update<<<kRedBlocks, kRedThreads, 0, st>>>(n, k->sc, k->v, k->v_old, k->u, k->u_old, k->r,
-                                                                k->z, k->partials, dist_owned_mask(ctx), done);
-            LAUNCH_CHECK(ctx);
-            finish_reduction(ctx, k, done, st);
-            k_minres_rotate<<<1, 32, 0, st>>>(k->red, k->sc, k->fl);
-            LAUNCH_CHECK(ctx);
-            k_minres_finalize<<<grid_for(n, 256), 256, 0, st>>>(n, k->sc, k->xi, k->w1, k->w2, k->v, k->v_old, k->u,
-                                                                k->u_old, k->r, k->z, done);
-            LAUNCH_CHECK(ctx);
-            k_commit<<<1, 1, 0, st>>>(k->fl);
-            LAUNCH_CHECK(ctx);
+            if (eager) seg(3); else run(3);
         }
         CUDA_CHECK(cudaMemcpyAsync(k->h_fl, k->fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(k->h_sc, k->sc, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
@@ -474,6 +544,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     }
     to_api(ctx, k->xi, x, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+    dist_check(ctx);
     prof_collect(ctx);
     info[0] = (double)k->h_fl[F_ITERS];
     info[1] = (double)k->h_fl[F_CONV];
@@ -483,6 +554,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     // KSPConvergedReason-style code: 2 rtol/atol reached, -3 iteration limit, -4 breakdown, -5 stagnation
     info[5] = k->h_fl[F_CONV] ? 2.0 : (k->h_fl[F_BREAKDOWN] ? -4.0 : (k->h_fl[F_STAG] ? -5.0 : -3.0));
     info[6] = k->h_sc[S_BNORM];
+    info[7] = k->h_sc[S_BTRUE];
 }
 
 // ---------------------------------------------------------------------------------- GMRES(m)
@@ -523,7 +595,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
     int iters = 0;
     bool converged = false;
-    double norm0 = -1, norm = 0, tol = 0, bnorm = 0;
+    double norm0 = -1, norm = 0, tol = 0, bnorm = 0, btrue = 0;
     {   // PETSc default with a nonzero initial guess: tolerance relative to ||B b||_2 (left preconditioning)
         eliminated_rhs(ctx, k, st);
         pc_apply_dist(ctx, k->r, k->z, nullptr, st);
@@ -543,6 +615,8 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         if (norm0 < 0) {
             norm0 = beta;
             if (!(bnorm > 0.0)) bnorm = beta;
+            btrue = bnorm;
+            if (ctx->norm_mode == 1) bnorm = std::min(bnorm, beta);
             tol = std::max(ctx->rtol * bnorm, ctx->atol);
         }
         norm = beta;
@@ -610,6 +684,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     }
     to_api(ctx, k->xi, x, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+    dist_check(ctx);
     info[0] = iters;
     info[1] = converged ? 1.0 : 0.0;
     info[2] = bnorm > 0 ? norm / bnorm : 0.0;
@@ -617,11 +692,23 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     info[4] = 0.0;
     info[5] = converged ? 2.0 : -3.0;
     info[6] = bnorm;
+    info[7] = btrue;
 }
 
 void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
     MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run before mpet_solve");
     for (int i = 0; i < 8; ++i) info[i] = 0.0;
+    if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+        // the legacy default stream cannot be captured into a CUDA graph: solve on a stream of our own, ordered
+        // after everything the caller has queued (the solve is synchronous, so nothing has to be ordered after it)
+        if (!ctx->solve_stream) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->solve_stream, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ctx->solve_event, cudaEventDisableTiming));
+        }
+        CUDA_CHECK(cudaEventRecord(ctx->solve_event, st));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->solve_stream, ctx->solve_event, 0));
+        st = ctx->solve_stream;
+    }
     if (ctx->method == 0) minres(ctx, b, x, info, st);
     else gmres(ctx, b, x, info, st);
 }

@@ -170,6 +170,7 @@ void export_values(mpet_ctx* ctx, int which, double* out, cudaStream_t st) {
 }
 
 void set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, cudaStream_t st) {
+    ctx->graph_epoch++;               // mask pointers / presence are baked into captured launches
     if (ctx->bc_dofs) { dev_free(ctx, ctx->bc_dofs); dev_free(ctx, ctx->bc_vals); dev_free(ctx, ctx->bc_dofs_int); }
     if (!ctx->bc_mask) ctx->bc_mask = dev_alloc<uint8_t>(ctx, ctx->N);
     if (!ctx->bc_mask_int) ctx->bc_mask_int = dev_alloc<uint8_t>(ctx, ctx->Nint);

@@ -148,10 +148,12 @@ class Engine:
                                         _ptr(x), _ptr(y), float(beta), self._stream()))
 
     # ------------------------------------------------------------------ Krylov
-    def krylov_setup(self, method="minres", pc="amg", rtol=1e-5, atol=1e-50, maxit=10000, restart=30):
+    def krylov_setup(self, method="minres", pc="amg", rtol=1e-5, atol=1e-50, maxit=10000, restart=30,
+                     reference_norm="b"):
         m = {"minres": 0, "gmres": 1}[method]
         p = {"none": 0, "jacobi": 1, "amg": 2}[pc]
         self._ck(self.lib.mpet_krylov_setup(self._ctx, m, p, float(rtol), float(atol), int(maxit), int(restart)))
+        self._ck(self.lib.mpet_krylov_reference_norm(self._ctx, {"b": 0, "min_b_r0": 1}[reference_norm]))
 
     def pc_setup(self):
         self._ck(self.lib.mpet_pc_setup(self._ctx, self._stream()))
@@ -160,7 +162,7 @@ class Engine:
         info = (C.c_double * 8)()
         self._ck(self.lib.mpet_solve(self._ctx, _ptr(b), _ptr(x), info, self._stream()))
         return dict(niter=int(info[0]), converged=bool(info[1]), rel_res=float(info[2]), res0=float(info[3]),
-                    breakdown=bool(info[4]), reason=int(info[5]), bnorm=float(info[6]))
+                    breakdown=bool(info[4]), reason=int(info[5]), refnorm=float(info[6]), bnorm=float(info[7]))
 
     def pc_apply(self, r, z):
         self._ck(self.lib.mpet_pc_apply(self._ctx, _ptr(r), _ptr(z), self._stream()))
@@ -196,8 +198,15 @@ class Engine:
         """Read (and optionally reset/switch) the library's CUDA-event profile."""
         out = (C.c_double * 16)()
         self._ck(self.lib.mpet_profile(self._ctx, int(enable), out))
-        names = ["spmv", "pc", "vec", "assemble", "rhs", "comm"]
+        names = ["spmv", "pc", "vec", "assemble", "rhs", "comm", "pc_u", "pc_p"]
         return {n: dict(ms=float(out[i]), count=int(out[8 + i])) for i, n in enumerate(names)}
+
+    def pc_bytes(self):
+        return int(self.lib.mpet_pc_bytes(self._ctx))
+
+    def comm_kind(self):
+        return {0: "single GPU", 1: "NCCL send/recv", 2: "peer-memory (NVLink stores + flags)"}[
+            int(self.lib.mpet_comm_kind(self._ctx))]
 
     def device_bytes(self):
         return int(self.lib.mpet_device_bytes(self._ctx))

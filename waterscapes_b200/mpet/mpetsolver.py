@@ -347,6 +347,7 @@ class MPETSolver(object):
                                      absolute_tolerance=self.params["krylov_atol"],
                                      maximum_iterations=self.params["krylov_maxit"], nonzero_initial_guess=True)
         b = self._rhs(time, float(time), float(dt), theta, bcs)
+        self._last_b = b                          # kept for residual checks (bench.py: true_residual)
         self.up.x.copy_(self.up_.x)               # initial guess; boundary entries are overwritten
         krylov.set_operators(A, None)
         niter = krylov.solve(self.up.vector(), b)

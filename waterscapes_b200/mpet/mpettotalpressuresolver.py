@@ -160,6 +160,7 @@ class MPETTotalPressureSolver(MPETSolver):
                                      absolute_tolerance=self.params["krylov_atol"],
                                      maximum_iterations=self.params["krylov_maxit"], nonzero_initial_guess=True)
         b, _ = self._rhs(time, float(time), float(dt), theta, bcs)
+        self._last_b = b
         self.up.x.copy_(self.up_.x)
         krylov.set_operators(A, None)
         niter = krylov.solve(self.up.vector(), b)
