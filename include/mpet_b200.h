@@ -68,6 +68,12 @@ int mpet_set_params_total_pressure(mpet_ctx* ctx, double E, double nu, const dou
                                    const double* K_host, const double* S_host, const double* c_host,
                                    double dt, double theta);
 
+/* Spatially varying permeability: K of P1 field `field` as a DG0 function, one value per cell,
+ * as in the reference's sandbox/biot-robin/three_fields_precond.py:263-271 (`K = Function(DG0)`).  The scalar K
+ * passed to mpet_set_params for that field then acts as a multiplier (pass 1.0).  values_dev f64[Nc] (copied) or
+ * NULL to return to the constant.  Assemble (lhs and prec) again afterwards. */
+int mpet_set_cell_coefficient(mpet_ctx* ctx, int field, const double* values_dev, void* stream);
+
 /* ---- matrix assembly ---------------------------------------------------------------------------
  * mpet_assemble_lhs  : A = assemble(a)                       (mpetsolver.py:335,412,496; form :196-201,260)
  * mpet_add_entries   : A.axpy(1.0, assemble(a_robin[i]))     (mpetsolver.py:336-338; form :252-253)
@@ -141,6 +147,19 @@ int mpet_pc_setup(mpet_ctx* ctx, void* stream);
 int mpet_solve(mpet_ctx* ctx, const double* b_dev, double* x_dev, double* info_host, void* stream);
 /* apply the preconditioner once: z = M^-1 r (tests) */
 int mpet_pc_apply(mpet_ctx* ctx, const double* r_dev, double* z_dev, void* stream);
+
+/* ---- nullspace handling: Lagrange multipliers as a dense border -------------------------
+ * Replaces the Real-space components the reference appends to its mixed space when the displacement is only
+ * determined up to rigid motions (u_has_nullspace) or a pressure up to a constant (p_has_nullspace):
+ * mpetsolver.py:115-124 (spaces), :203-215 (r_i (Z_i, u) + z_i (Z_i, v), p_i q_null + p_null q_i), with the rigid
+ * motions Z_i of rm_basis_L2.py:10-74.  The nb <= 16 dense rows/columns stay OUTSIDE the CSR matrix: the solver
+ * iterates on K = [A C; C^T 0] with column i of C = columns_dev[i*N .. (i+1)*N) (e.g. the mass matrix applied to the
+ * nodal values of Z_i).  With a border, every vector passed to mpet_solve has N + nb entries, multipliers last.
+ * mpet_set_prec_shift adds shift_u (u, v) and shift_p[i] (p_i, q_i) to the blocks of the preconditioner (the
+ * reference's commented-out `inner(u, v)*dx` term, mpetsolver.py:276-277, and `p[k]*q[k]*dx`, :274): without
+ * essential boundary conditions those blocks are singular.  Call it before mpet_assemble_prec. */
+int mpet_set_border(mpet_ctx* ctx, int nb, const double* columns_dev, void* stream);
+int mpet_set_prec_shift(mpet_ctx* ctx, double shift_u, const double* shift_p_host);
 
 /* ---- multi-GPU (one process per GPU; rows owned by rank, ghost entries exchanged over NVLink) ---
  * Replaces what DOLFIN + PETSc do under mpirun (src/mpet/utils/jobscript.sh:43): VecScatter halo

@@ -361,7 +361,10 @@ class BlockAMG:
     components (p-coarsened to P1, then aggregation) + one hierarchy per P1 field, which degenerates to a
     Chebyshev polynomial on the whole spectrum when the field's block is well conditioned (amg.cu)."""
 
-    def __init__(self, oracle, dirichlet_dofs):
+    def __init__(self, oracle, dirichlet_dofs, light=False):
+        """``light``: one cycle with degree-2 smoothing for the P1 fields that keep a hierarchy (what the CUDA
+        library does for relative tolerances >= 1e-8, amg.cu: g_p_degree / krylov.cu: light_tolerance), and
+        degree-1 smoothing in the displacement cycle (amg.cu: g_u_degree)."""
         o = oracle
         sp_ = o.space
         assert o.d == 3 and sp_.nreal == 0 and sp_.perm is None
@@ -390,12 +393,12 @@ class BlockAMG:
                     if not m2[v]:
                         rows.append(r); cols.append(v); vals.append(0.5)
         P21 = sp.csr_matrix((vals, (rows, cols)), shape=(N2, Nv))
-        self.u = ScalarAMG(A2, first_coarse=(P21, A1))
+        self.u = ScalarAMG(A2, first_coarse=(P21, A1), degree=1 if light else None)
         self.p = []
         for i in range(A):
             d = sp_.p_dofs(i)
-            self.p.append(ScalarAMG(_eliminate(P[d][:, d], mask[d]), allow_polynomial=True, cycles=P1_CYCLES,
-                                    degree=P1_DEGREE))
+            self.p.append(ScalarAMG(_eliminate(P[d][:, d], mask[d]), allow_polynomial=True,
+                                    cycles=1 if light else P1_CYCLES, degree=2 if light else P1_DEGREE))
         self.N2, self.Nv, self.A = N2, Nv, A
 
     def __call__(self, r):

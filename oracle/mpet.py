@@ -120,7 +120,10 @@ class MPETOracle:
         A = self.A
         self.E, self.nu = float(params["E"]), float(params["nu"])
         self.alpha = [float(v) for v in params["alpha"]]
-        self.K = [float(v) for v in params["K"]]
+        # K_i: a number, or an array with one value per cell (DG0 permeability, as in the reference's
+        # sandbox/biot-robin/three_fields_precond.py:263-271)
+        self.K_cell = {i: np.asarray(v, dtype=float) for i, v in enumerate(params["K"]) if np.ndim(v) == 1}
+        self.K = [float(np.mean(v)) for v in params["K"]]
         self.c = [float(v) for v in params["c"]]
         self.S = np.array(params["S"], dtype=float).reshape(A, A)
         self.dt, self.theta, self.t, self.T = float(dt), float(theta), float(t), float(T)
@@ -214,6 +217,12 @@ class MPETOracle:
         N1, dN1 = tabulate(d, 1, pts)
         return pts, wts, N2, dN2, N1, dN1
 
+    def _Kc(self, i, cells):
+        """K_i on ``cells``: the scalar, or its DG0 values broadcast over the element matrix."""
+        if i in self.K_cell:
+            return self.K_cell[i][cells][:, None, None]
+        return self.K[i]
+
     def element_blocks(self, cells):
         """Per-cell integrals used by every form (degree-2 exact)."""
         d = self.d
@@ -252,7 +261,7 @@ class MPETOracle:
                 Ae[:, pi:pi + n1, k * n2:(k + 1) * n2] = \
                     -self.alpha[i] * np.swapaxes(D[:, :, :, k], 1, 2)
             offsum = sum(self.S[i, j] for j in range(A) if j != i)
-            Ae[:, pi:pi + n1, pi:pi + n1] = (-self.c[i] * M - dt * th * self.K[i] * Lp
+            Ae[:, pi:pi + n1, pi:pi + n1] = (-self.c[i] * M - dt * th * self._Kc(i, cells) * Lp
                                              - dt * th * offsum * M)
             for j in range(A):
                 if j != i:
@@ -275,7 +284,7 @@ class MPETOracle:
                 Be[:, pi:pi + n1, k * n2:(k + 1) * n2] = \
                     -self.alpha[i] * np.swapaxes(D[:, :, :, k], 1, 2)
             offsum = sum(self.S[i, j] for j in range(A) if j != i)
-            Be[:, pi:pi + n1, pi:pi + n1] = (-self.c[i] * M + dt * (1 - th) * self.K[i] * Lp
+            Be[:, pi:pi + n1, pi:pi + n1] = (-self.c[i] * M + dt * (1 - th) * self._Kc(i, cells) * Lp
                                              + dt * (1 - th) * offsum * M)
             for j in range(A):
                 if j != i:
@@ -301,7 +310,7 @@ class MPETOracle:
             mass = self.c[i] + dt * th * offsum
             if total_pressure_mass:
                 mass += self.alpha[i] ** 2 / lmbda
-            Pe[:, pi:pi + n1, pi:pi + n1] = mass * M + dt * th * self.K[i] * Lp
+            Pe[:, pi:pi + n1, pi:pi + n1] = mass * M + dt * th * self._Kc(i, cells) * Lp
         return Pe
 
     # ------------------------------------------------------------------ global assembly
@@ -665,7 +674,7 @@ def _solve_iterative(self, rtol=1e-5, atol=1e-50, maxit=10000, monitor=None, rea
     A = self.assemble_lhs()
     B = self.assemble_prev_operator()
     dofs, _ = self.dirichlet(self.t)
-    M = BlockAMG(self, dofs)
+    M = BlockAMG(self, dofs, light=rtol >= 1e-8)
     mask = np.zeros(self.space.N, dtype=bool)
     mask[dofs] = True
     self.up = self.up_.copy()
@@ -735,7 +744,7 @@ class MPETTotalPressureOracle(MPETOracle):
                 pj = d * n2 + (j + 1) * n1
                 blk = -(self.alpha[i] * self.alpha[j] / lmbda) * M
                 if j == i:
-                    blk = blk - self.c[i] * M - dt * th * self.K[i] * Lp - dt * th * offsum * M
+                    blk = blk - self.c[i] * M - dt * th * self._Kc(i, cells) * Lp - dt * th * offsum * M
                 else:
                     blk = blk + dt * th * self.S[i, j] * M
                 Ae[:, pi:pi + n1, pj:pj + n1] = blk
@@ -759,7 +768,7 @@ class MPETTotalPressureOracle(MPETOracle):
                 pj = d * n2 + (j + 1) * n1
                 blk = -(self.alpha[i] * self.alpha[j] / lmbda) * M
                 if j == i:
-                    blk = blk - self.c[i] * M + dt * (1 - th) * self.K[i] * Lp + dt * (1 - th) * offsum * M
+                    blk = blk - self.c[i] * M + dt * (1 - th) * self._Kc(i, cells) * Lp + dt * (1 - th) * offsum * M
                 else:
                     blk = blk - dt * (1 - th) * self.S[i, j] * M
                 Be[:, pi:pi + n1, pj:pj + n1] = blk
@@ -783,5 +792,5 @@ class MPETTotalPressureOracle(MPETOracle):
             pi = d * n2 + (i + 1) * n1
             offsum = sum(self.S[i, j] for j in range(J) if j != i)
             mass = self.alpha[i] ** 2 / lmbda + self.c[i] + dt * th * offsum
-            Pe[:, pi:pi + n1, pi:pi + n1] = mass * M + dt * th * self.K[i] * Lp
+            Pe[:, pi:pi + n1, pi:pi + n1] = mass * M + dt * th * self._Kc(i, cells) * Lp
         return Pe

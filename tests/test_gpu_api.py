@@ -143,3 +143,102 @@ def test_step_and_iterative_branch():
     u, p0, p1 = solver.up.split(deepcopy=True)
     assert u.values.shape == (o.space.N2, 3) and p0.values.shape == (o.space.Nv,)
     assert abs(p0((0.5, 0.5, 0.5)) - float(p0.values[np.argmin(np.linalg.norm(mesh.coordinates - 0.5, axis=1))])) < 0.5
+
+
+def test_dg0_permeability_matches_oracle():
+    """K_0 as a DG0 (cell-wise constant) function, the reference's
+    sandbox/biot-robin/three_fields_precond.py:263-271, through MPETSolver: assembled A, preconditioner blocks,
+    previous-state load (theta = 0.5 puts K into the right-hand side as well) and two time steps against the
+    oracle's cell-wise restatement."""
+    from waterscapes_b200.mpet import (MPETProblem, MPETSolver, UnitCubeMesh, Constant, Expression, CompiledSubDomain,
+                                       CellFunction, assemble)
+    n, J, theta, dt, T = 4, 2, 0.5, 0.1, 0.2
+    mesh = UnitCubeMesh(n)
+    rng = np.random.default_rng(11)
+    kvals = 10.0 ** rng.uniform(-3, 0, mesh.num_cells())          # three decades of contrast
+    base = dict(J=J, E=2.2, nu=0.4545, alpha=(0.5, 0.5), c=(1.0, 1.0), S=((0.0, 1.0), (1.0, 0.0)))
+    time = Constant(0.0)
+    problem = MPETProblem(mesh, time, params=dict(base, K=(CellFunction(mesh, kvals), 0.3)))
+    problem.p_bar = [Expression("%d*sin(pi*x[0])*sin(2*pi*t)" % (i + 1), t=time, degree=1) for i in range(J)]
+    problem.g = [Expression("(1+%d)*x[0]*x[1]*cos(t)" % i, t=time, degree=1) for i in range(J)]
+    on_boundary = CompiledSubDomain("on_boundary")
+    on_boundary.mark(problem.momentum_boundary_markers, 0)
+    for i in range(J):
+        on_boundary.mark(problem.continuity_boundary_markers[i], 0)
+    solver = MPETSolver(problem, dict(dt=dt, theta=theta, T=T))
+    o = MPETOracle(unit_cube_mesh(n), dict(base, K=(kvals, 0.3)), dt=dt, theta=theta, T=T)
+    o.p_bar = [Coef(fn=lambda x, t, i=i: (i + 1) * np.sin(PI * x[:, 0]) * np.sin(2 * PI * t)) for i in range(J)]
+    o.g = [Coef(fn=lambda x, t, i=i: (1 + i) * x[:, 0] * x[:, 1] * np.cos(t), degree=1) for i in range(J)]
+    o.momentum_markers[:] = 0
+    for i in range(J):
+        o.continuity_markers[i][:] = 0
+    _init(solver, o)
+    A = solver._assemble_system().to_scipy()
+    assert _rel(A.data, o.on_pattern(o.assemble_lhs()).data) < 1e-12
+    P = assemble(solver.prec).to_scipy()
+    Po = o.on_pattern(o.assemble_prec())
+    assert _rel(P.data, Po.data) < 1e-12                       # no Dirichlet set pushed yet: P as assembled
+    bd = torch.empty(o.space.N, dtype=torch.float64, device="cuda")
+    solver.engine.rhs_prev(solver.up_.x, bd)
+    assert _rel(bd.cpu().numpy(), o.assemble_L()) < 1e-12
+    ref = [up.copy() for up, t in o.solve_direct()]
+    for k, (up, t) in enumerate(solver.solve()):
+        x = up.vector().get_local()
+        sp_ = o.space
+        nu = 3 * sp_.N2
+        errs = [_rel(x[:nu], ref[k][:nu])] + [_rel(x[sp_.p_dofs(i)], ref[k][sp_.p_dofs(i)]) for i in range(J)]
+        assert max(errs) < 1e-8, (k, errs)
+    # back to a constant: the weighted stiffness is dropped again
+    problem.params["K"] = (0.05, 0.3)
+    A2 = solver._assemble_system().to_scipy()
+    o2 = MPETOracle(unit_cube_mesh(n), dict(base, K=(0.05, 0.3)), dt=dt, theta=theta, T=T)
+    assert _rel(A2.data, o2.on_pattern(o2.assemble_lhs()).data) < 1e-12
+
+
+def test_hdf5_mesh_and_marker_ingestion(tmp_path):
+    """a mesh and its facet markers written in DOLFIN's HDF5 layout, read back the way the
+    reference's brain script does (MPET-4networks-colin27.py:28-45), and a step solved on the ingested mesh
+    reproduces the step on the original one; fields are stored with HDF5File.write(u, "/u", t) (:257-259)."""
+    from waterscapes_b200.mpet import (MPETProblem, MPETSolver, Mesh, MeshFunction, BoxMesh, Constant, Expression,
+                                       CompiledSubDomain, HDF5File)
+    from waterscapes_b200.mpet.hdf5 import H5Reader
+    mesh0 = BoxMesh((0.0, 0.0, 0.0), (2.0, 1.0, 1.0), 4, 3, 3)
+    bnd0 = MeshFunction("size_t", mesh0, 2)
+    bnd0.set_all(1)
+    CompiledSubDomain("on_boundary && near(x[0], 0.0)").mark(bnd0, 2)
+    path = str(tmp_path / "box_boundaries.h5")
+    with HDF5File(None, path, "w") as f:
+        f.write(mesh0, "/mesh")
+        f.write(bnd0, "/boundaries")
+
+    def run(mesh, boundaries):
+        time = Constant(0.0)
+        params = dict(J=1, E=500.0, nu=0.35, alpha=(1.0,), c=(1e-2,), K=(1e-2,), S=((0.0,),))
+        problem = MPETProblem(mesh, time, params=params)
+        problem.p_bar = [Expression("x[0]*t", t=time, degree=1)]
+        arr = boundaries.array()
+        problem.momentum_boundary_markers.array()[:] = np.where(arr == 2, 0, 1)      # clamp the x = 0 face
+        problem.continuity_boundary_markers[0].array()[:] = 0
+        solver = MPETSolver(problem, dict(dt=0.1, T=0.1, theta=1.0))
+        for up, t in solver.solve():
+            pass
+        return solver, up
+
+    mesh = Mesh()
+    f = HDF5File(None, path, "r")
+    f.read(mesh, "/mesh", False)
+    boundaries = MeshFunction("size_t", mesh, 2)
+    f.read(boundaries, "/boundaries")
+    f.close()
+    assert np.array_equal(mesh.cells, mesh0.cells) and np.array_equal(mesh.coordinates, mesh0.coordinates)
+    assert np.array_equal(boundaries.array(), bnd0.array()) and set(np.unique(bnd0.array())) == {1, 2}
+    s0, up0 = run(mesh0, bnd0)
+    s1, up1 = run(mesh, boundaries)
+    assert np.array_equal(up0.vector().get_local(), up1.vector().get_local())
+    out = str(tmp_path / "u.h5")
+    with HDF5File(None, out, "w") as g:
+        g.write(up1.split(deepcopy=True)[0], "/u", 0.1)
+        g.write(up1, "/up", 0.1)
+    r = H5Reader(out)
+    assert np.array_equal(r.read("/up/vector_0"), up1.vector().get_local())
+    assert abs(r.attrs("/u/vector_0")["timestamp"] - 0.1) < 1e-15

@@ -30,6 +30,7 @@ PROTOTYPES = {
                                C.POINTER(_f64), _f64, _f64]),
     "mpet_set_params_total_pressure": (_int, [_c_ctx, _f64, _f64, C.POINTER(_f64), C.POINTER(_f64), C.POINTER(_f64),
                                               C.POINTER(_f64), _f64, _f64]),
+    "mpet_set_cell_coefficient": (_int, [_c_ctx, _int, _p, _p]),
     "mpet_assemble_lhs": (_int, [_c_ctx, _p]),
     "mpet_add_entries": (_int, [_c_ctx, _p, _p, _p, _i64, _p]),
     "mpet_assemble_prec": (_int, [_c_ctx, _p]),
@@ -47,6 +48,8 @@ PROTOTYPES = {
     "mpet_pc_setup": (_int, [_c_ctx, _p]),
     "mpet_solve": (_int, [_c_ctx, _p, _p, C.POINTER(_f64), _p]),
     "mpet_pc_apply": (_int, [_c_ctx, _p, _p, _p]),
+    "mpet_set_border": (_int, [_c_ctx, _int, _p, _p]),
+    "mpet_set_prec_shift": (_int, [_c_ctx, _f64, C.POINTER(_f64)]),
     "mpet_attach_comm": (_int, [_c_ctx, _p, _int, _int]),
     "mpet_nccl_unique_id": (_int, [_p]),
     "mpet_set_halo": (_int, [_c_ctx, _int, C.POINTER(_int), C.POINTER(_i64), _p, C.POINTER(_i64), _p, _p, _p]),

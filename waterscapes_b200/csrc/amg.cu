@@ -190,7 +190,7 @@ k_spmm_plain(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* _
 __global__ void __launch_bounds__(256)
 k_masked_copy(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
               const double* __restrict__ in, double scale, const uint8_t* __restrict__ mask,
-              double* __restrict__ out, double* __restrict__ dinv) {
+              double* __restrict__ out, double* __restrict__ dinv, const double* __restrict__ in2, double scale2) {
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
     int lane = threadIdx.x & 7;
     if (row >= nrows) return;
@@ -198,6 +198,7 @@ k_masked_copy(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* 
     for (int32_t t = rowptr[row] + lane; t < rowptr[row + 1]; t += 8) {
         int32_t c = cols[t];
         double v = scale * in[t];
+        if (in2) v += scale2 * in2[t];
         if (rd) v = (c == row) ? 1.0 : 0.0;
         else if (mask && mask[c]) v = 0.0;
         out[t] = v;
@@ -557,6 +558,7 @@ const int kChebDegree = 2;
 // Chebyshev polynomial on the WHOLE spectrum instead of a V-cycle (oracle/krylov.py: same constants)
 const double kPolyKappaMax = 12.0;
 const double kPolyTarget = 1.0e-4;
+const double kPolyTargetLight = 1.0e-4;    // light mode (loose tolerances): residual-polynomial target of the polynomial fields
 const int kPolyMaxDegree = 16;
 const int kLanczosSteps = 40;
 // Galerkin operators of the aggregated levels: entries below kDropTol * sqrt(a_ii a_jj) are lumped into the diagonal.
@@ -571,6 +573,8 @@ const double kDropTol = 0.01;
 // 3 cycles: 350 / 1989; 2 cycles, degree 4: 341 / 1942; 4 cycles: 340 / 1995 (plateau = exact block solves).
 const int kP1Cycles = 2;
 const int kP1Degree = 4;
+const int kP1DegreeCoarse = 4;
+const int kP1DegreeLight = 2;
 // multi-GPU: the transition to the replicated levels uses plain aggregation (weaker coarse correction); measured
 // at N = 2 (91^3): 2 cycles 541-600 iterations / 4417 ms, 3 cycles 473 / 3981, 4 cycles 462 / 4241
 const int kP1CyclesDist = 3;
@@ -630,9 +634,27 @@ static bool skip_redundant_halos() {
     return v;
 }
 
-static int g_p_degree() {
-    static const int d = []() { const char* e = getenv("MPET_P_DEGREE"); return e ? std::max(1, atoi(e)) : kP1Degree; }();
-    return d;
+// "Light" P1-field cycles (one cycle, degree-2 smoothing) for loose tolerances: MINRES' first ~100 iterations are
+// insensitive to how accurately the (cheap, latency-bound) P1 blocks are inverted -- measured on cfg5 at the bench
+// tolerance: 62/68/71/71 iterations with 1 cycle of degree 2 exactly as with 2 or 3 cycles of degree 4, 5.5 % less time
+// per step on one GPU and ~2 ms less per iteration on two --, while tight tolerances (the LU stand-in) need the strong
+// cycles (r01: 549 iterations with 1 cycle of degree 2, 341 with 2 cycles of degree 4).  krylov.cu picks the mode
+// from the relative tolerance; oracle/krylov.py BlockAMG(light=...) is the same rule.
+static int g_p_degree(const mpet_ctx* ctx) {
+    static const int d = []() { const char* e = getenv("MPET_P_DEGREE"); return e ? std::max(1, atoi(e)) : 0; }();
+    return d ? d : (ctx->pc_light ? kP1DegreeLight : kP1Degree);
+}
+// displacement cycle: degree-2 Chebyshev smoothing, degree 1 (damped Jacobi) in light mode -- measured on cfg5 at the
+// bench tolerance: 63/69/72/73 iterations instead of 62/68/71/71 with HALF the P2-level passes (2 instead of 4 per
+// application): 288 instead of 355 ms per step
+static int g_u_degree(const mpet_ctx* ctx) {
+    static const int d = []() { const char* e = getenv("MPET_U_DEGREE"); return e ? std::max(1, atoi(e)) : 0; }();
+    return d ? d : (ctx->pc_light ? 1 : kChebDegree);
+}
+// smoothing degree on the aggregated (non-mesh) levels of the P1-field hierarchies
+static int g_p_degree_coarse(const mpet_ctx* ctx) {
+    static const int d = []() { const char* e = getenv("MPET_P_DEGREE_COARSE"); return e ? std::max(1, atoi(e)) : 0; }();
+    return d ? d : (ctx->pc_light ? kP1DegreeLight : kP1DegreeCoarse);
 }
 
 template <int W>
@@ -645,7 +667,7 @@ void chebyshev(mpet_ctx* ctx, AmgLevel& L, const double* b, const double* x_in, 
     double rho_old = 1.0 / sigma;
     double* buf[2] = {L.x, L.t};
     const double* cur = x_in;
-    const int steps = degree > 0 ? degree : (W == 1 ? g_p_degree() : kChebDegree);
+    const int steps = degree > 0 ? degree : (W == 1 ? (L.is_mesh_level ? g_p_degree(ctx) : g_p_degree_coarse(ctx)) : g_u_degree(ctx));
     for (int k = 0; k < steps; ++k) {
         bool last = (k == steps - 1);
         double* dst = last ? x_out : buf[k & 1];
@@ -680,7 +702,8 @@ void vcycle(mpet_ctx* ctx, AmgHierarchy& H, int lev, const double* b, double* x,
     AmgLevel& L = H.levels[lev];
     const int64_t n = L.A.nrows;
     if (H.poly_degree > 0) {       // polynomial mode: no hierarchy
-        chebyshev<W>(ctx, L, b, nullptr, x, done, st, H.poly_lo, H.poly_hi, H.poly_degree);
+        chebyshev<W>(ctx, L, b, nullptr, x, done, st, H.poly_lo, H.poly_hi,
+                     ctx->pc_light ? H.poly_degree_light : H.poly_degree);
         return;
     }
     if (lev == (int)H.levels.size() - 1) {
@@ -854,11 +877,11 @@ void lanczos_bounds(mpet_ctx* ctx, AmgLevel& L, const uint8_t* own_dev, double& 
     cudaFree(v); cudaFree(vp); cudaFree(w); cudaFree(sc);
 }
 
-int poly_degree_for(double lo, double hi) {
+int poly_degree_for(double lo, double hi, double target = kPolyTarget) {
     const double kappa = hi / lo;
     const double sigma = (std::sqrt(kappa) - 1.0) / (std::sqrt(kappa) + 1.0);
     int k = 1;
-    while (k < kPolyMaxDegree && 2.0 * std::pow(sigma, k) / (1.0 + std::pow(sigma, 2 * k)) > kPolyTarget) ++k;
+    while (k < kPolyMaxDegree && 2.0 * std::pow(sigma, k) / (1.0 + std::pow(sigma, 2 * k)) > target) ++k;
     return k;
 }
 
@@ -1084,13 +1107,14 @@ void finish_hierarchy(mpet_ctx* ctx, AmgHierarchy& H, cudaStream_t st) {
 }
 
 DevCsr masked_block(mpet_ctx* ctx, const NodeGraph& g, const double* vals, double scale, const uint8_t* mask,
-                    double** dinv_out, cudaStream_t st) {
+                    double** dinv_out, cudaStream_t st, const double* vals2 = nullptr, double scale2 = 0.0) {
     DevCsr M;
     M.nrows = g.nrows; M.ncols = g.ncols; M.nnz = g.nnz;
     M.rowptr = g.rowptr; M.col = g.col;
     M.val = dev_alloc<double>(ctx, g.nnz);
     *dinv_out = dev_alloc<double>(ctx, g.nrows);
-    k_masked_copy<<<grid_for(g.nrows * 8, 256), 256, 0, st>>>(g.nrows, g.rowptr, g.col, vals, scale, mask, M.val, *dinv_out);
+    k_masked_copy<<<grid_for(g.nrows * 8, 256), 256, 0, st>>>(g.nrows, g.rowptr, g.col, vals, scale, mask, M.val, *dinv_out,
+                                                              scale2 != 0.0 ? vals2 : nullptr, scale2);
     LAUNCH_CHECK(ctx);
     return M;
 }
@@ -1149,6 +1173,7 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
     MPET_REQUIRE(ctx->prec_ready, "mpet_assemble_prec must run before mpet_pc_setup");
     amg_free(ctx);                    // a new dt / new Dirichlet set rebuilds the hierarchies
     ctx->graph_epoch++;               // captured iterations hold pointers into the old hierarchies
+    ctx->border_scaled = false;       // c_i . B c_i of the multiplier block belongs to the old hierarchy
     struct ArenaGuard {
         mpet_ctx* c;
         explicit ArenaGuard(mpet_ctx* c_) : c(c_) { c->arena = &c->amg_allocs; }
@@ -1176,13 +1201,16 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         AmgHierarchy* H = new AmgHierarchy();
         H->nrhs = 4;   // W = 4: three components + pad
         AmgLevel L0;
-        L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->coef.p_mu, ctx->bc_mask, &L0.dinv, st);
+        // + shift (u, v): the displacement block without essential boundary conditions (u_has_nullspace) is singular
+        const double shift = ctx->prec_shift_u;
+        if (shift != 0.0) ensure_m22(ctx, st);
+        L0.A = masked_block(ctx, ctx->g22, ctx->k22, ctx->coef.p_mu, ctx->bc_mask, &L0.dinv, st, ctx->m22, shift);
         if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P2W4;
         sync_ghost_diagonal(ctx, L0, true, st);
         H->levels.push_back(L0);
         AmgLevel L1;
         L1.A = masked_block(ctx, ctx->g11, ctx->l11, ctx->coef.p_mu, ctx->bc_mask /* vertices are the first Nv nodes */,
-                            &L1.dinv, st);
+                            &L1.dinv, st, ctx->m11, shift);
         if (dist_active(ctx)) L1.halo_plan = DIST_PLAN_P1W4;
         sync_ghost_diagonal(ctx, L1, false, st);
         HostCsr P = p2_to_p1(nv, ctx->Ne, edge_v, mask2);
@@ -1206,6 +1234,7 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         AmgHierarchy* H = new AmgHierarchy();
         H->nrhs = 1;
         AmgLevel L0;
+        L0.is_mesh_level = true;
         L0.A = masked_block(ctx, ctx->g11, ctx->pp11 + (int64_t)i * ctx->g11.nnz, 1.0,
                             ctx->bc_mask + 3 * n2 + (int64_t)i * nv, &L0.dinv, st);
         if (dist_active(ctx)) L0.halo_plan = DIST_PLAN_P1W1;
@@ -1219,6 +1248,8 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         const double lo = 0.97 * lmin, hi = 1.02 * lmax;
         if (lmin > 0 && hi / lo <= kPolyKappaMax && !getenv("MPET_NO_POLY")) {
             H->poly_degree = poly_degree_for(lo, hi);
+            static const double light_target = []() { const char* e = getenv("MPET_POLY_TARGET_LIGHT"); return e ? atof(e) : kPolyTargetLight; }();
+            H->poly_degree_light = poly_degree_for(lo, hi, light_target);
             H->poly_lo = lo;
             H->poly_hi = hi;
         } else {
@@ -1268,7 +1299,7 @@ static void amg_apply_impl(mpet_ctx* ctx, const double* r, double* z, const int*
     static const int p_cycles = []() { const char* e = getenv("MPET_P_CYCLES"); return e ? std::max(1, atoi(e)) : 0; }();
     static const int u_cycles = []() { const char* e = getenv("MPET_U_CYCLES"); return e ? std::max(1, atoi(e)) : 1; }();
     const bool fork = want_streams && ctx->A > 0 && !dist_active(ctx);
-    const int p_cyc = p_cycles > 0 ? p_cycles : (dist_active(ctx) ? kP1CyclesDist : kP1Cycles);
+    const int p_cyc = p_cycles > 0 ? p_cycles : (ctx->pc_light ? 1 : (dist_active(ctx) ? kP1CyclesDist : kP1Cycles));
     if (fork) {
         if (ctx->pc_streams_ready < ctx->A) {
             int lo = 0, hi = 0;

@@ -276,6 +276,29 @@ int mpet_set_params_total_pressure(mpet_ctx* ctx, double E, double nu, const dou
     MPET_CATCH(ctx)
 }
 
+int mpet_set_cell_coefficient(mpet_ctx* ctx, int field, const double* values_dev, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->Nc > 0, "mpet_set_mesh must be called first");
+    MPET_REQUIRE(field >= 0 && field < ctx->A, "field index out of range");
+    cudaStream_t st = as_stream(stream);
+    if (values_dev) {
+        if (!ctx->kcell[field]) {
+            ctx->kcell[field] = dev_alloc<double>(ctx, ctx->Nc);
+            ctx->l11w[field] = dev_alloc<double>(ctx, ctx->g11.nnz);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(ctx->kcell[field], values_dev, sizeof(double) * ctx->Nc, cudaMemcpyDeviceToDevice, st));
+    } else if (ctx->kcell[field]) {
+        dev_free(ctx, ctx->kcell[field]);
+        dev_free(ctx, ctx->l11w[field]);
+        ctx->kcell[field] = nullptr;
+        ctx->l11w[field] = nullptr;
+    }
+    ctx->cell_coef_dirty = true;
+    ctx->lhs_ready = false;
+    ctx->prec_ready = false;
+    MPET_CATCH(ctx)
+}
+
 int mpet_assemble_lhs(mpet_ctx* ctx, void* stream) {
     MPET_TRY(ctx)
     cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
@@ -401,6 +424,32 @@ int mpet_krylov_reference_norm(mpet_ctx* ctx, int mode) {
     MPET_TRY(ctx)
     MPET_REQUIRE(mode == 0 || mode == 1, "mode: 0 = |b| (PETSc default), 1 = min(|b|, |r0|)");
     ctx->norm_mode = mode;
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_border(mpet_ctx* ctx, int nb, const double* columns_dev, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->N > 0, "mpet_set_mesh must be called first");
+    MPET_REQUIRE(nb >= 0 && nb <= 16, "0..16 multipliers");
+    cudaStream_t st = as_stream(stream);
+    if (ctx->border) { dev_free(ctx, ctx->border); ctx->border = nullptr; }
+    ctx->nb = nb;
+    ctx->border_scaled = false;
+    ctx->graph_epoch++;
+    if (nb > 0) {
+        ctx->border = dev_alloc<double>(ctx, (int64_t)nb * ctx->Nint);
+        for (int i = 0; i < nb; ++i)
+            to_internal(ctx, columns_dev + (int64_t)i * ctx->N, ctx->border + (int64_t)i * ctx->Nint, st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    MPET_CATCH(ctx)
+}
+
+int mpet_set_prec_shift(mpet_ctx* ctx, double shift_u, const double* shift_p_host) {
+    MPET_TRY(ctx)
+    ctx->prec_shift_u = shift_u;
+    for (int i = 0; i < ctx->A; ++i) ctx->prec_shift_p[i] = shift_p_host ? shift_p_host[i] : 0.0;
+    ctx->prec_ready = false;           // the P1 blocks are re-formed by the next mpet_assemble_prec
     MPET_CATCH(ctx)
 }
 

@@ -88,6 +88,11 @@ struct AsmCoefs {
     double cup[MPET_MAX_NETWORKS], cpu[MPET_MAX_NETWORKS], cl[MPET_MAX_NETWORKS];
     double cm[MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
 };
+// DG0 permeability: per-cell values kc[f] (null: constant) and where the weighted stiffness of field f is kept
+struct CellCoefs {
+    const double* kc[MPET_MAX_NETWORKS];
+    double* lw[MPET_MAX_NETWORKS];
+};
 
 __global__ void k_geometry(const double* __restrict__ coords, const int32_t* __restrict__ cells,
                            int64_t nc, double* __restrict__ geom) {
@@ -264,14 +269,17 @@ __global__ void __launch_bounds__(256)
 k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
         const uint32_t* __restrict__ glist, const double* __restrict__ geom,
         const int32_t* __restrict__ rp12, const int64_t* __restrict__ rowptr, int64_t n2, int64_t nv,
-        int64_t nnz11, int A, const AsmCoefs K, double* __restrict__ vals, double* __restrict__ m11,
-        double* __restrict__ l11) {
+        int64_t nnz11, int A, const AsmCoefs K, const CellCoefs CC, double* __restrict__ vals,
+        double* __restrict__ m11, double* __restrict__ l11) {
     const double* cm = K.cm;
     const double* cl = K.cl;
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz11) return;
     int64_t v = row_of_entry(rp11, nv, (int32_t)e);
     double M = 0, L = 0;
+    double Lw[MPET_MAX_NETWORKS];
+#pragma unroll
+    for (int f = 0; f < MPET_MAX_NETWORKS; ++f) Lw[f] = 0.0;
     int32_t g1 = gptr[e + 1];
     for (int32_t g = gptr[e]; g < g1; ++g) {
         uint32_t id = glist[g];
@@ -288,10 +296,16 @@ k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
             double gn = c_GL[n * 3] * Ji[x] + c_GL[n * 3 + 1] * Ji[3 + x] + c_GL[n * 3 + 2] * Ji[6 + x];
             s += gm * gn;
         }
-        L += det * s * (1.0 / 6.0);
+        const double lc = det * s * (1.0 / 6.0);
+        L += lc;
+#pragma unroll
+        for (int f = 0; f < MPET_MAX_NETWORKS; ++f)
+            if (f < A && CC.kc[f]) Lw[f] += CC.kc[f][c] * lc;        // same fixed order: deterministic
     }
     m11[e] = M;
     l11[e] = L;
+    for (int f = 0; f < A; ++f)
+        if (CC.kc[f]) CC.lw[f][e] = Lw[f];
     if (vals == nullptr) return;
     int32_t d12 = rp12[v + 1] - rp12[v];
     int32_t d11 = rp11[v + 1] - rp11[v];
@@ -300,20 +314,20 @@ k_asm11(const int32_t* __restrict__ rp11, const int32_t* __restrict__ gptr,
         int64_t base = rowptr[3 * n2 + i * nv + v] + 3 * (int64_t)d12 + jj;
         for (int j = 0; j < A; ++j) {
             double val = cm[i * A + j] * M;
-            if (i == j) val += cl[i] * L;
+            if (i == j) val += cl[i] * (CC.kc[i] ? Lw[i] : L);
             vals[base + (int64_t)j * d11] = val;
         }
     }
 }
 
 __global__ void k_prec11(const double* __restrict__ m11, const double* __restrict__ l11, int64_t nnz11,
-                         int A, const AsmCoefs K, double* __restrict__ pp11) {
+                         int A, const AsmCoefs K, const CellCoefs CC, double* __restrict__ pp11) {
     const double* cm = K.cup;      // slots re-used: pm in cup, pk in cpu
     const double* ck = K.cpu;
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz11) return;
     double M = m11[e], L = l11[e];
-    for (int i = 0; i < A; ++i) pp11[i * nnz11 + e] = cm[i] * M + ck[i] * L;
+    for (int i = 0; i < A; ++i) pp11[i * nnz11 + e] = cm[i] * M + ck[i] * (CC.kc[i] ? CC.lw[i][e] : L);
 }
 
 }  // namespace
@@ -355,6 +369,12 @@ static int asm22_grid(mpet_ctx* ctx, int64_t n2) {
     return (int)std::min<int64_t>(grid_for(n2 * 32, 256), (int64_t)ctx->sm_count * 4);
 }
 
+static CellCoefs cell_coefs(mpet_ctx* ctx) {
+    CellCoefs CC;
+    for (int f = 0; f < MPET_MAX_NETWORKS; ++f) { CC.kc[f] = ctx->kcell[f]; CC.lw[f] = ctx->l11w[f]; }
+    return CC;
+}
+
 void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
     MPET_REQUIRE(ctx->params_set, "mpet_set_params must be called before assembly");
     const int A = ctx->A;
@@ -382,7 +402,7 @@ void assemble_lhs(mpet_ctx* ctx, cudaStream_t st) {
         LAUNCH_CHECK(ctx);
         k_asm11<<<grid_for(ctx->g11.nnz, threads), threads, 0, st>>>(
             ctx->g11.rowptr, ctx->g11.gptr, ctx->g11.glist, ctx->geom, ctx->g12.rowptr, ctx->rowptr, n2, nv,
-            ctx->g11.nnz, A, K, ctx->vals, ctx->m11, ctx->l11);
+            ctx->g11.nnz, A, K, cell_coefs(ctx), ctx->vals, ctx->m11, ctx->l11);
         LAUNCH_CHECK(ctx);
     }
     ctx->lhs_ready = true;
@@ -408,16 +428,17 @@ void assemble_prec(mpet_ctx* ctx, cudaStream_t st) {
         LAUNCH_CHECK(ctx);
     }
     if (A == 0) { ctx->prec_ready = true; return; }
-    if (!ctx->lhs_ready) {   // m11 / l11 not yet computed
+    if (!ctx->lhs_ready || ctx->cell_coef_dirty) {   // m11 / l11 (/ weighted stiffness) not yet computed
         k_asm11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(
             ctx->g11.rowptr, ctx->g11.gptr, ctx->g11.glist, ctx->geom, ctx->g12.rowptr, ctx->rowptr, ctx->N2,
-            ctx->Nv, ctx->g11.nnz, A, AsmCoefs(), nullptr, ctx->m11, ctx->l11);
+            ctx->Nv, ctx->g11.nnz, A, AsmCoefs(), cell_coefs(ctx), nullptr, ctx->m11, ctx->l11);
         LAUNCH_CHECK(ctx);
     }
     if (!ctx->pp11) ctx->pp11 = dev_alloc<double>(ctx, (int64_t)A * ctx->g11.nnz);
     AsmCoefs K;                           // mpetsolver.py:270-271 / mpettotalpressuresolver.py:279-282
-    for (int i = 0; i < MPET_MAX_NETWORKS; ++i) { K.cup[i] = ctx->coef.pm[i]; K.cpu[i] = ctx->coef.pk[i]; }
-    k_prec11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(ctx->m11, ctx->l11, ctx->g11.nnz, A, K, ctx->pp11);
+    for (int i = 0; i < MPET_MAX_NETWORKS; ++i) { K.cup[i] = ctx->coef.pm[i] + ctx->prec_shift_p[i]; K.cpu[i] = ctx->coef.pk[i]; }
+    k_prec11<<<grid_for(ctx->g11.nnz, 256), 256, 0, st>>>(ctx->m11, ctx->l11, ctx->g11.nnz, A, K, cell_coefs(ctx), ctx->pp11);
     LAUNCH_CHECK(ctx);
+    ctx->cell_coef_dirty = false;
     ctx->prec_ready = true;
 }

@@ -66,6 +66,7 @@ struct AmgLevel {
     double* t = nullptr;
     double lambda_max = 0.0;  // estimate of rho(D^-1 A)
     int halo_plan = -1;       // >= 0: level vectors are distributed (owned + ghost rows), refreshed with this plan
+    bool is_mesh_level = false;   // finest level of a P1-field hierarchy (smoothing degree kP1Degree; coarser: kP1DegreeCoarse)
     SpmmPlan planA, planP, planR;   // staged-kernel chunk tables (nchunks == 0: not staged)
 };
 
@@ -76,6 +77,7 @@ struct AmgHierarchy {
     int64_t coarse_n = 0;
     // polynomial mode (well-conditioned block): the whole "cycle" is poly_degree Chebyshev steps on [poly_lo, poly_hi]
     int poly_degree = 0;
+    int poly_degree_light = 0;     // ... in light mode (ctx->pc_light)
     double* cyc_r = nullptr;       // work vectors of multi-cycle applications (development aid)
     double* cyc_e = nullptr;
     double poly_lo = 0.0, poly_hi = 0.0;
@@ -144,6 +146,11 @@ struct mpet_ctx {
     double* m22 = nullptr;       // [nnz22] P2 mass (lazy)
     double* k22 = nullptr;       // [nnz22] P2 stiffness (grad,grad) (prec, lazy)
     double* pp11 = nullptr;      // [A*nnz11] preconditioner pressure blocks
+    // DG0 (cell-wise constant) permeability of a P1 field: per-cell values and the stiffness
+    // weighted with them; fields without one use l11 times their scalar K
+    double* kcell[MPET_MAX_NETWORKS] = {};   // [Nc]
+    double* l11w[MPET_MAX_NETWORKS] = {};    // [nnz11]
+    bool cell_coef_dirty = false;
 
     // coefficients
     double E = 0, nu = 0, mu = 0, lmbda = 0, dt = 0, theta = 1;
@@ -165,9 +172,18 @@ struct mpet_ctx {
     BlockPlan plan_u, plan_p;         // chunk tables of the staged block SpMV
     bool staged_ok = false;
 
+    // Lagrange multipliers bordering the system (nullspace handling)
+    int nb = 0;                      // number of multipliers (<= 16)
+    double* border = nullptr;        // [nb][Nint] columns c_i in the solver-internal layout
+    double* border_scale = nullptr;  // [16] c_i . B c_i
+    bool border_scaled = false;
+    double prec_shift_u = 0.0;       // + shift * (u, v) in the displacement block of the preconditioner
+    double prec_shift_p[MPET_MAX_NETWORKS] = {};   // + shift_i * (p_i, q_i)
+
     // Krylov
     int method = 0, pc = 2, maxit = 10000, restart = 30;
     double rtol = 1e-5, atol = 1e-50;
+    bool pc_light = false;       // light P1-field cycles (amg.cu): set per solve from rtol
     int norm_mode = 0;           // reference norm of the convergence test: 0 = |b|_B (PETSc default), 1 = min(|b|_B, |r0|_B)
     struct KrylovWork* kw = nullptr;
     struct DistState* dist = nullptr;           // NCCL communicator + halo plan (dist.cu)

@@ -25,6 +25,7 @@ void scatter_bc_values_int(mpet_ctx* ctx, double* out_int, cudaStream_t st);   /
 namespace {
 
 const int kRedBlocks = 1184;   // 148 SMs x 8
+const int kBorderPad = 16;     // entries appended to every Krylov vector when multipliers border the system
 const int kRedThreads = 256;
 
 enum {
@@ -279,6 +280,60 @@ __global__ void k_scale_copy(const double* __restrict__ src, double scale, int64
     if (i < n) dst[i] = src[i] * scale;
 }
 
+// ---------------------------------------------------------------------------------- bordered system (multipliers)
+// out[j] += sum_i mu_i c_i[j] on the non-Dirichlet rows j < n;  mu_i = in[n + i]
+__global__ void k_border_axpy(int64_t n, int nb, const double* __restrict__ C, const double* __restrict__ in,
+                              double* __restrict__ out, const uint8_t* __restrict__ mask, const int* __restrict__ done) {
+    if (done && *done) return;
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n || (mask && mask[j])) return;
+    double acc = out[j];
+    for (int i = 0; i < nb; ++i) acc += in[n + i] * C[(int64_t)i * n + j];
+    out[j] = acc;
+}
+
+// partials[i][block] of c_i . in[0..n)
+__global__ void __launch_bounds__(kRedThreads)
+k_border_dots(int64_t n, int nb, const double* __restrict__ C, const double* __restrict__ in,
+              double* __restrict__ partials, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sm[32];
+    for (int i = 0; i < nb; ++i) {
+        double s = 0.0;
+        for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+            s += C[(int64_t)i * n + j] * in[j];
+        s = block_reduce_sum(s, sm);
+        if (threadIdx.x == 0) partials[i * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// out[n + i] = c_i . in   (fixed summation order); the pad entries behind the multipliers stay zero
+__global__ void __launch_bounds__(kRedThreads)
+k_border_final(int64_t n, int nb, int npad, const double* __restrict__ partials, int nparts, double* __restrict__ out,
+               const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sm[32];
+    for (int i = 0; i < npad; ++i) {
+        double s = 0.0;
+        if (i < nb) s = final_sum(partials + (int64_t)i * nparts, nparts, sm);
+        if (threadIdx.x == 0) out[n + i] = s;
+        __syncthreads();
+    }
+}
+
+// z[n + i] = r[n + i] / s_i : the multiplier block of the preconditioner (Schur-complement scale s_i = c_i . B c_i)
+__global__ void k_border_pc(int64_t n, int nb, int npad, const double* __restrict__ scale, const double* __restrict__ r,
+                            double* __restrict__ z, const int* __restrict__ done) {
+    if (done && *done) return;
+    int i = threadIdx.x;
+    if (i < npad) z[n + i] = i < nb ? r[n + i] / scale[i] : 0.0;
+}
+
+__global__ void k_copy_tail(int nb, int npad, const double* __restrict__ src, double* __restrict__ dst) {
+    int i = threadIdx.x;
+    if (i < npad) dst[i] = i < nb ? src[i] : 0.0;
+}
+
 }  // namespace
 
 struct KrylovWork {
@@ -298,13 +353,35 @@ struct KrylovWork {
     int64_t graph_key = -1;
 };
 
+static void drop_graphs(KrylovWork* k) {
+    for (auto& g : k->graph)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    k->graph_key = -1;
+}
+
 static KrylovWork* get_work(mpet_ctx* ctx) {
-    if (ctx->kw && ctx->kw->n == ctx->Nint) return ctx->kw;
-    MPET_REQUIRE(ctx->kw == nullptr, "context size changed");
-    KrylovWork* k = new KrylovWork();
-    k->n = ctx->Nint;     // all Krylov vectors live in the solver-internal layout (layout.cuh)
+    // all Krylov vectors live in the solver-internal layout (layout.cuh), followed -- when Lagrange multipliers
+    // border the system -- by kBorderPad entries that hold the multipliers
+    const int64_t need = ctx->Nint + (ctx->nb > 0 ? kBorderPad : 0);
+    if (ctx->kw && ctx->kw->n == need) return ctx->kw;
+    if (ctx->kw) {
+        KrylovWork* o = ctx->kw;
+        drop_graphs(o);
+        double* old[] = {o->r, o->z, o->v, o->v_old, o->u, o->u_old, o->w1, o->w2, o->xi, o->bi, o->basis};
+        for (double* q : old)
+            if (q) dev_free(ctx, q);
+        o->basis = nullptr;
+        o->basis_m = 0;
+    }
+    KrylovWork* k = ctx->kw ? ctx->kw : new KrylovWork();
+    const bool fresh = ctx->kw == nullptr;
+    k->n = need;
     double** vecs[] = {&k->r, &k->z, &k->v, &k->v_old, &k->u, &k->u_old, &k->w1, &k->w2, &k->xi, &k->bi};
-    for (auto p : vecs) *p = dev_alloc<double>(ctx, ctx->Nint);
+    for (auto p : vecs) {
+        *p = dev_alloc<double>(ctx, need);
+        CUDA_CHECK(cudaMemset(*p, 0, sizeof(double) * need));
+    }
+    if (!fresh) return k;
     k->partials = dev_alloc<double>(ctx, (int64_t)kRedBlocks * 8);
     k->sc = dev_alloc<double>(ctx, S_COUNT);
     k->red = dev_alloc<double>(ctx, 8);
@@ -314,12 +391,6 @@ static KrylovWork* get_work(mpet_ctx* ctx) {
     CUDA_CHECK(cudaMallocHost(&k->h_fl, sizeof(int) * F_COUNT));
     ctx->kw = k;
     return k;
-}
-
-static void drop_graphs(KrylovWork* k) {
-    for (auto& g : k->graph)
-        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-    k->graph_key = -1;
 }
 
 void krylov_free(mpet_ctx* ctx) {
@@ -366,6 +437,28 @@ static void pc_apply_dist(mpet_ctx* ctx, const double* r, double* z, const int* 
     // the V-cycles exchange their own halos level by level (amg.cu); one more refresh covers Jacobi / none
     pc_apply_flag(ctx, r, z, done, st);
     if (dist_active(ctx) && ctx->pc != 2) dist_halo(ctx, DIST_PLAN_KRYLOV, z, false, done, st);
+    if (ctx->nb > 0) {      // multiplier block: diagonal, Schur-complement scale (border_setup)
+        k_border_pc<<<1, 32, 0, st>>>(ctx->Nint, ctx->nb, kBorderPad, ctx->border_scale, r, z, done);
+        LAUNCH_CHECK(ctx);
+    }
+}
+
+// y = K x for the (possibly bordered) system  K = [A C; C^T 0]  (mpetsolver.py:203-215: the Real-space Lagrange
+// multipliers of the rigid motions / pressure constants are 6 + k dense rows and columns kept OUTSIDE the CSR
+// matrix).  Dirichlet rows are identity rows; Krylov vectors vanish there, so the dots run over
+// all entries while the column update skips the masked rows.
+static void apply_operator(mpet_ctx* ctx, KrylovWork* k, const double* x, double* y, const uint8_t* mask,
+                           const int* done, cudaStream_t st) {
+    block_spmv(ctx, x, y, mask, done, st);
+    if (ctx->nb == 0) return;
+    const int64_t n = ctx->Nint;
+    k_border_axpy<<<grid_for(n, 256), 256, 0, st>>>(n, ctx->nb, ctx->border, x, y, mask, done);
+    LAUNCH_CHECK(ctx);
+    const int G = 296;
+    k_border_dots<<<G, kRedThreads, 0, st>>>(n, ctx->nb, ctx->border, x, k->partials, done);
+    LAUNCH_CHECK(ctx);
+    k_border_final<<<1, kRedThreads, 0, st>>>(n, ctx->nb, kBorderPad, k->partials, G, y, done);
+    LAUNCH_CHECK(ctx);
 }
 
 static void ensure_scratch(mpet_ctx* ctx) {
@@ -374,7 +467,14 @@ static void ensure_scratch(mpet_ctx* ctx) {
 }
 
 // API-layout entry points (tests / measurement): convert, run the production kernels, convert back
+// loose tolerances take the light P1-field cycles (amg.cu); MPET_PC_LIGHT=0/1 forces the mode
+static bool light_tolerance(const mpet_ctx* ctx) {
+    static const int forced = []() { const char* e = getenv("MPET_PC_LIGHT"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    return forced >= 0 ? forced == 1 : ctx->rtol >= 1e-8;
+}
+
 void pc_apply(mpet_ctx* ctx, const double* r, double* z, cudaStream_t st) {
+    ctx->pc_light = light_tolerance(ctx);
     ensure_scratch(ctx);
     to_internal(ctx, r, ctx->scratch_int[0], st);
     pc_apply_flag(ctx, ctx->scratch_int[0], ctx->scratch_int[1], nullptr, st);
@@ -411,7 +511,7 @@ static void initial_residual(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
     if (ctx->n_bc > 0) scatter_bc_values_int(ctx, k->xi, st);
     dist_halo(ctx, DIST_PLAN_KRYLOV, k->xi, false, nullptr, st);      // ghosts of x and b come from their owners
     dist_halo(ctx, DIST_PLAN_KRYLOV, k->bi, false, nullptr, st);
-    block_spmv(ctx, k->xi, k->v, nullptr, nullptr, st);
+    apply_operator(ctx, k, k->xi, k->v, nullptr, nullptr, st);
     k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr, k->n, k->r,
                                                     nullptr);
     LAUNCH_CHECK(ctx);
@@ -427,7 +527,7 @@ static void eliminated_rhs(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
         scatter_bc_values_int(ctx, k->w1, st);
         dist_halo(ctx, DIST_PLAN_KRYLOV, k->w1, false, nullptr, st);
         dist_halo(ctx, DIST_PLAN_KRYLOV, k->bi, false, nullptr, st);
-        block_spmv(ctx, k->w1, k->v, nullptr, nullptr, st);
+        apply_operator(ctx, k, k->w1, k->v, nullptr, nullptr, st);
         k_residual<<<grid_for(k->n, 256), 256, 0, st>>>(k->bi, k->v, ctx->bc_mask_int, k->n, k->r, k->w1);
         LAUNCH_CHECK(ctx);
     } else {
@@ -437,12 +537,60 @@ static void eliminated_rhs(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
     dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);
 }
 
+// API vectors carry the multipliers behind the N finite-element dofs (as the reference's mixed space does)
+static void load_system(mpet_ctx* ctx, KrylovWork* k, const double* b, const double* x, cudaStream_t st) {
+    to_internal(ctx, b, k->bi, st);
+    to_internal(ctx, x, k->xi, st);
+    if (ctx->nb > 0) {
+        k_copy_tail<<<1, 32, 0, st>>>(ctx->nb, kBorderPad, b + ctx->N, k->bi + ctx->Nint);
+        LAUNCH_CHECK(ctx);
+        k_copy_tail<<<1, 32, 0, st>>>(ctx->nb, kBorderPad, x + ctx->N, k->xi + ctx->Nint);
+        LAUNCH_CHECK(ctx);
+    }
+}
+
+static void store_solution(mpet_ctx* ctx, KrylovWork* k, double* x, cudaStream_t st) {
+    to_api(ctx, k->xi, x, st);
+    if (ctx->nb > 0)
+        CUDA_CHECK(cudaMemcpyAsync(x + ctx->N, k->xi + ctx->Nint, sizeof(double) * ctx->nb, cudaMemcpyDeviceToDevice, st));
+}
+
+// Schur-complement scale of the multiplier block of the preconditioner: s_i = c_i . B c_i (once per hierarchy)
+static void border_setup(mpet_ctx* ctx, KrylovWork* k, cudaStream_t st) {
+    if (ctx->nb == 0 || ctx->border_scaled) return;
+    MPET_REQUIRE(!dist_active(ctx), "Lagrange-multiplier borders are single-GPU for now");
+    if (!ctx->border_scale) ctx->border_scale = dev_alloc<double>(ctx, kBorderPad);
+    std::vector<double> s(kBorderPad, 1.0);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->border_scale, s.data(), sizeof(double) * kBorderPad, cudaMemcpyHostToDevice, st));
+    const int64_t n = ctx->Nint;
+    for (int i = 0; i < ctx->nb; ++i) {
+        CUDA_CHECK(cudaMemsetAsync(k->v, 0, sizeof(double) * k->n, st));
+        CUDA_CHECK(cudaMemcpyAsync(k->v, ctx->border + (int64_t)i * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        if (ctx->n_bc > 0) {       // the columns act on the free rows only
+            k_residual<<<grid_for(n, 256), 256, 0, st>>>(k->v, k->u_old, ctx->bc_mask_int, n, k->v, nullptr);
+            LAUNCH_CHECK(ctx);
+        }
+        pc_apply_flag(ctx, k->v, k->u, nullptr, st);
+        k_dot_partial<<<kRedBlocks, kRedThreads, 0, st>>>(k->v, k->u, n, k->partials, nullptr, nullptr);
+        LAUNCH_CHECK(ctx);
+        k_final_store<<<1, kRedThreads, 0, st>>>(k->partials, kRedBlocks, k->red, nullptr);
+        LAUNCH_CHECK(ctx);
+        CUDA_CHECK(cudaMemcpyAsync(&s[i], k->red, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        MPET_REQUIRE(s[i] > 0.0, "a multiplier column is zero or the preconditioner is not positive on it");
+    }
+    CUDA_CHECK(cudaMemcpyAsync(ctx->border_scale, s.data(), sizeof(double) * kBorderPad, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    ctx->border_scaled = true;
+}
+
 static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
     KrylovWork* k = get_work(ctx);
     const int64_t n = k->n;
     const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
-    to_internal(ctx, b, k->bi, st);
-    to_internal(ctx, x, k->xi, st);
+    CUDA_CHECK(cudaMemsetAsync(k->u_old, 0, sizeof(double) * k->n, st));
+    border_setup(ctx, k, st);
+    load_system(ctx, k, b, x, st);
     eliminated_rhs(ctx, k, st);                              // reference norm sqrt(b . B b) -> red[1]
     pc_apply_dist(ctx, k->r, k->z, nullptr, st);
     dot_to(ctx, k, k->r, k->z, nullptr, st);
@@ -462,7 +610,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     auto seg = [&](int which) {
         switch (which) {
             case 0:
-                block_spmv(ctx, k->u, k->r, mask, done, st);
+                apply_operator(ctx, k, k->u, k->r, mask, done, st);
                 break;
             case 1:
                 dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, done, st);
@@ -494,7 +642,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
     // (hierarchy, Dirichlet set, peer arena: ctx->graph_epoch).  NCCL halos are not captured.
     static const bool want_graphs = []() { const char* e = getenv("MPET_GRAPHS"); return !(e && e[0] == '0'); }();
     const bool can_graph = want_graphs && (!dist_active(ctx) || dist_comm_kind(ctx) == 2);
-    const int64_t key = ctx->graph_epoch * 8 + ctx->pc;
+    const int64_t key = ctx->graph_epoch * 16 + ctx->pc * 2 + (ctx->pc_light ? 1 : 0);
     if (k->graph_key != key) drop_graphs(k);
     auto capture = [&](int slot) {
         ctx->prof_suspended = true;
@@ -542,7 +690,7 @@ static void minres(mpet_ctx* ctx, const double* b, double* x, double* info, cuda
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (k->h_fl[F_DONE] || enq >= ctx->maxit) break;
     }
-    to_api(ctx, k->xi, x, st);
+    store_solution(ctx, k, x, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     dist_check(ctx);
     prof_collect(ctx);
@@ -590,8 +738,9 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     }
     const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
     double* V = k->basis;
-    to_internal(ctx, b, k->bi, st);
-    to_internal(ctx, x, k->xi, st);
+    CUDA_CHECK(cudaMemsetAsync(k->u_old, 0, sizeof(double) * k->n, st));
+    border_setup(ctx, k, st);
+    load_system(ctx, k, b, x, st);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
     int iters = 0;
     bool converged = false;
@@ -628,7 +777,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         int j = 0;
         for (; j < m && iters < ctx->maxit; ++j) {
             double* w = V + (int64_t)(j + 1) * ldv;
-            block_spmv(ctx, V + (int64_t)j * ldv, k->r, mask, nullptr, st);
+            apply_operator(ctx, k, V + (int64_t)j * ldv, k->r, mask, nullptr, st);
             dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);      // ghost rows of the local matrix are incomplete
             pc_apply_dist(ctx, k->r, w, nullptr, st);
             // classical Gram-Schmidt, two passes (CGS2)
@@ -682,7 +831,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
         }
         if (jj == 0) break;
     }
-    to_api(ctx, k->xi, x, st);
+    store_solution(ctx, k, x, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     dist_check(ctx);
     info[0] = iters;
@@ -698,6 +847,7 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
 void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
     MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run before mpet_solve");
     for (int i = 0; i < 8; ++i) info[i] = 0.0;
+    ctx->pc_light = light_tolerance(ctx);
     if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
         // the legacy default stream cannot be captured into a CUDA graph: solve on a stream of our own, ordered
         // after everything the caller has queued (the solve is synchronous, so nothing has to be ordered after it)

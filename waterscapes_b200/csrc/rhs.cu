@@ -15,7 +15,10 @@
 
 namespace {
 
-struct PrevCoefs { double c[2 * MPET_MAX_NETWORKS + MPET_MAX_NETWORKS * MPET_MAX_NETWORKS]; };
+struct PrevCoefs {
+    double c[2 * MPET_MAX_NETWORKS + MPET_MAX_NETWORKS * MPET_MAX_NETWORKS];
+    const double* lw[MPET_MAX_NETWORKS];      // DG0-weighted stiffness of a field (null: l11)
+};
 
 __global__ void __launch_bounds__(256)
 k_rhs_prev(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
@@ -42,7 +45,7 @@ k_rhs_prev(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
     const double* pbase = up + 3 * n2;
     for (int32_t e = rp11[v] + lane; e < rp11[v + 1]; e += 32) {
         int32_t vp = col11[e];
-        double M = m11[e], L = l11[e];
+        double M = m11[e], L = K.lw[i] ? K.lw[i][e] : l11[e];
         double acc = coef[A + i] * L * pbase[(int64_t)i * nv + vp];
         for (int j = 0; j < A; ++j) acc += coef[2 * A + i * A + j] * M * pbase[(int64_t)j * nv + vp];
         sum += acc;
@@ -139,6 +142,7 @@ void rhs_prev(mpet_ctx* ctx, const double* up, double* b, cudaStream_t st) {
     if (A == 0) return;
     PrevCoefs K;
     double* coef = K.c;
+    for (int f = 0; f < MPET_MAX_NETWORKS; ++f) K.lw[f] = ctx->kcell[f] ? ctx->l11w[f] : nullptr;
     for (int i = 0; i < A; ++i) {
         coef[i] = ctx->coef.ru[i];
         coef[A + i] = ctx->coef.rl[i];
@@ -173,7 +177,10 @@ void set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, cudaStrea
     ctx->graph_epoch++;               // mask pointers / presence are baked into captured launches
     if (ctx->bc_dofs) { dev_free(ctx, ctx->bc_dofs); dev_free(ctx, ctx->bc_vals); dev_free(ctx, ctx->bc_dofs_int); }
     if (!ctx->bc_mask) ctx->bc_mask = dev_alloc<uint8_t>(ctx, ctx->N);
-    if (!ctx->bc_mask_int) ctx->bc_mask_int = dev_alloc<uint8_t>(ctx, ctx->Nint);
+    if (!ctx->bc_mask_int) {      // + the pad behind the multipliers of a bordered system (never masked)
+        ctx->bc_mask_int = dev_alloc<uint8_t>(ctx, ctx->Nint + 64);
+        CUDA_CHECK(cudaMemsetAsync(ctx->bc_mask_int, 0, ctx->Nint + 64, st));
+    }
     ctx->bc_dofs_int = dev_alloc<int32_t>(ctx, n);
     CUDA_CHECK(cudaMemsetAsync(ctx->bc_mask_int, 0, ctx->Nint, st));
     ctx->n_bc = n;

@@ -97,6 +97,15 @@ class Engine:
         self._ck(self.lib.mpet_set_params_total_pressure(self._ctx, float(E), float(nu), arr(alpha, J), arr(K, J),
                                                          arr(S, J * J), arr(c, J), float(dt), float(theta)))
 
+    def set_cell_coefficient(self, field, values):
+        """DG0 permeability of P1 field ``field``: one value per cell, or None for the constant."""
+        if values is None:
+            self._ck(self.lib.mpet_set_cell_coefficient(self._ctx, int(field), C.c_void_p(0), self._stream()))
+            return
+        v = self._dev(values, torch.float64)
+        assert v.numel() == self.sizes["Nc"]
+        self._ck(self.lib.mpet_set_cell_coefficient(self._ctx, int(field), _ptr(v), self._stream()))
+
     def assemble_lhs(self):
         self._ck(self.lib.mpet_assemble_lhs(self._ctx, self._stream()))
 
@@ -154,6 +163,22 @@ class Engine:
         p = {"none": 0, "jacobi": 1, "amg": 2}[pc]
         self._ck(self.lib.mpet_krylov_setup(self._ctx, m, p, float(rtol), float(atol), int(maxit), int(restart)))
         self._ck(self.lib.mpet_krylov_reference_norm(self._ctx, {"b": 0, "min_b_r0": 1}[reference_norm]))
+
+    def set_border(self, columns):
+        """columns: [nb, N] device tensor (or None / empty to remove the border)."""
+        if columns is None or columns.numel() == 0:
+            self._ck(self.lib.mpet_set_border(self._ctx, 0, C.c_void_p(0), self._stream()))
+            self.nb = 0
+            return
+        cols = self._dev(columns, torch.float64)
+        assert cols.shape[1] == self.sizes["N"]
+        self._ck(self.lib.mpet_set_border(self._ctx, int(cols.shape[0]), _ptr(cols), self._stream()))
+        self.nb = int(cols.shape[0])
+
+    def set_prec_shift(self, shift_u, shift_p):
+        A = self.sizes["A"]
+        arr = (C.c_double * max(A, 1))(*[float(v) for v in shift_p])
+        self._ck(self.lib.mpet_set_prec_shift(self._ctx, float(shift_u), arr))
 
     def pc_setup(self):
         self._ck(self.lib.mpet_pc_setup(self._ctx, self._stream()))

@@ -6,9 +6,10 @@ _lib.load()
 
 from .dolfin_shim import (Mesh, BoxMesh, UnitCubeMesh, Constant, Expression, FacetNormal, MeshFunction,  # noqa
                           SubDomain, CompiledSubDomain, Function, FunctionSpace, DirichletBC, Parameters,
-                          parameters, interpolate, assign, info, warning, INVALID)
+                          parameters, interpolate, assign, info, warning, INVALID, CellFunction)
 from .la import assemble, LUSolver, PETScKrylovSolver, Matrix, Form  # noqa
 from .mpetproblem import MPETProblem, convert_to_E_nu, convert_to_mu_lmbda, elastic_stress  # noqa
 from .mpetsolver import MPETSolver, DIRICHLET_MARKER, NEUMANN_MARKER, ROBIN_MARKER  # noqa
 from .mpettotalpressuresolver import MPETTotalPressureSolver  # noqa
 from .bc_symmetric import get_bc_dofs, zero_rows_cols, apply_symmetric  # noqa
+from .hdf5 import HDF5File  # noqa

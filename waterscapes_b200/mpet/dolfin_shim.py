@@ -28,7 +28,12 @@ def warning(msg):
 class Mesh:
     """Tetrahedral mesh: coordinates f64[Nv,3], cells i32[Nc,4] (vertices ascending per cell)."""
 
-    def __init__(self, coordinates, cells):
+    def __init__(self, coordinates=None, cells=None):
+        self._facets = None
+        if coordinates is None:         # ``mesh = Mesh(); HDF5File(...).read(mesh, "/mesh", False)`` (hdf5.py)
+            self.coordinates = np.zeros((0, 3))
+            self.cells = np.zeros((0, 4), dtype=np.int32)
+            return
         self.coordinates = np.ascontiguousarray(coordinates, dtype=np.float64)
         self.cells = np.ascontiguousarray(np.sort(np.asarray(cells), axis=1), dtype=np.int32)
         assert self.coordinates.shape[1] == 3 and self.cells.shape[1] == 4, "the B200 path is 3-D (tets)"
@@ -125,6 +130,22 @@ class Constant:
     @property
     def is_constant(self):
         return True
+
+
+class CellFunction:
+    """A DG0 coefficient: one value per cell (``Function(FunctionSpace(mesh, "DG", 0))`` in the reference's
+    sandbox/biot-robin/three_fields_precond.py:263-271).  Accepted for the permeabilities ``params["K"][i]``."""
+
+    def __init__(self, mesh, values):
+        self.mesh = mesh
+        self.values = np.ascontiguousarray(values, dtype=float).reshape(-1)
+        assert self.values.shape[0] == mesh.num_cells()
+
+    def vector(self):
+        return self.values
+
+    def __float__(self):
+        raise TypeError("a DG0 coefficient has no single value")
 
 
 _NS = {k: getattr(np, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh",
@@ -349,8 +370,9 @@ class SubSpace:
 class FunctionSpace:
     """Layout of [P2]^3 x [P1]^J (UFC numbering, include/mpet_b200.h)."""
 
-    def __init__(self, mesh, J, engine):
+    def __init__(self, mesh, J, engine, nreal=0):
         self.mesh, self.J, self.engine = mesh, J, engine
+        self.nreal = int(nreal)          # Real-space (Lagrange multiplier) dofs appended behind the N finite-element dofs
         s = engine.sizes
         self.Nv, self.Ne, self.N2, self.N = s["Nv"], s["Ne"], s["N2"], s["N"]
         self._edges = None
@@ -362,6 +384,7 @@ class FunctionSpace:
         sorted vertex pair, exactly what graph.cu builds on the device.  Used by host-only logic/tests."""
         self = cls.__new__(cls)
         self.mesh, self.J, self.engine = mesh, J, None
+        self.nreal = 0
         c = mesh.cells.astype(np.int64)
         nv = mesh.num_vertices()
         pairs = np.concatenate([c[:, [a, b]] for a, b in ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))])
@@ -435,7 +458,7 @@ class Function:
     def __init__(self, space, tensor=None):
         self.space = space
         dev = space.engine.device
-        self.x = tensor if tensor is not None else torch.zeros(space.N, dtype=torch.float64, device=dev)
+        self.x = tensor if tensor is not None else torch.zeros(space.N + space.nreal, dtype=torch.float64, device=dev)
 
     def function_space(self):
         return self.space
@@ -453,7 +476,8 @@ class Function:
         return FunctionRef(self, i)
 
     def __len__(self):
-        return 1 + self.space.J
+        sp = self.space
+        return 1 + sp.J + ((1 if sp.nreal >= 6 else 0) + (sp.nreal - 6 if sp.nreal >= 6 else sp.nreal) if sp.nreal else 0)
 
     def split(self, deepcopy=True):
         a = self.x.detach().cpu().numpy()
@@ -462,6 +486,13 @@ class Function:
         for i in range(sp.J):
             lo, hi = sp.sub_range(i + 1)
             out.append(SubFunction(sp, i + 1, a[lo:hi].copy()))
+        if sp.nreal:      # (u, p_1..p_J, r, p_null...) as in the reference's mixed space (mpetsolver.py:121-128)
+            tail = a[sp.N:sp.N + sp.nreal]
+            nz = 6 if sp.nreal >= 6 else 0
+            if nz:
+                out.append(SubFunction(sp, -1, tail[:nz].copy()))
+            for k in range(nz, sp.nreal):
+                out.append(SubFunction(sp, -1, tail[k:k + 1].copy()))
         return tuple(out)
 
     def set_sub(self, index, data):

@@ -14,7 +14,7 @@ import torch
 
 from ..engine import Engine
 from .dolfin_shim import (Constant, Expression, NormalProduct, Function, FunctionSpace, DirichletBC,
-                          Parameters, info, warning)
+                          Parameters, CellFunction, info, warning)
 from .la import (Form, Matrix, AssembledVector, RobinEntries, FacetOperator, assemble, LUSolver,
                  PETScKrylovSolver, apply_symmetric, _is_zero, _M3, NEUMANN_MARKER as _N, ROBIN_MARKER as _R)
 from .mpetproblem import convert_to_mu_lmbda
@@ -38,9 +38,8 @@ class MPETSolver(object):
         if params is not None:
             self.params.update(params)
         self.solver_monitor = {}
-        if problem.u_has_nullspace or any(problem.p_has_nullspace):
-            raise NotImplementedError("nullspace Lagrange multipliers (Real spaces) are a 'next' row of the "
-                                      "hot-path scope (SURVEY.md 8f.2) and are not on the B200 path yet")
+        if (problem.u_has_nullspace or any(problem.p_has_nullspace)) and partition is not None:
+            raise NotImplementedError("nullspace Lagrange multipliers are single-GPU for now")
         if self.params["u_degree"] != 2 or self.params["p_degree"] != 1:
             raise NotImplementedError("the B200 kernels implement the Taylor-Hood pair P2-P1 only")
         self.engine = Engine(device)
@@ -51,6 +50,7 @@ class MPETSolver(object):
         self._prec_assembled_for = None
         self._facet_ops = {}
         self._lumped = {}
+        self._border_ready = False
         self.create_variational_forms()
         if self.partition is not None:
             self.partition.setup(self.engine, self.VQ, self.problem.mesh)
@@ -90,7 +90,11 @@ class MPETSolver(object):
         J = self._num_p1_fields()
         if self.engine.sizes is None:
             self.engine.set_mesh(mesh.coordinates, mesh.cells, J)
-        return FunctionSpace(mesh, J, self.engine)
+        # Real spaces of the reference (mpetsolver.py:115-124): six rigid-motion multipliers when the displacement has
+        # a nullspace, one multiplier per pressure that is only determined up to a constant.  They are appended to
+        # every dof vector and enter the solver as a dense border (mpet_set_border), not as CSR rows.
+        nreal = (6 if self.problem.u_has_nullspace else 0) + sum(bool(f) for f in self.problem.p_has_nullspace)
+        return FunctionSpace(mesh, J, self.engine, nreal=nreal)
 
     def create_variational_forms(self, include_preconditioner=False):
         mesh = self.problem.mesh
@@ -130,12 +134,20 @@ class MPETSolver(object):
     def _push_params(self):
         p = self.problem.params
         J = int(p["J"])
-        vals = (float(p["E"]), float(p["nu"]), [_f(v) for v in p["alpha"]], [_f(v) for v in p["K"]],
+        # a DG0 permeability travels as per-cell values; its scalar slot is then a multiplier of 1
+        dg0 = {i: v for i, v in enumerate(p["K"]) if isinstance(v, CellFunction)}
+        Ks = [1.0 if i in dg0 else _f(v) for i, v in enumerate(p["K"])]
+        cells_key = tuple((i, hash(v.values.tobytes())) for i, v in sorted(dg0.items()))
+        vals = (float(p["E"]), float(p["nu"]), [_f(v) for v in p["alpha"]], Ks,
                 [[_f(v) for v in row] for row in p["S"]], [_f(v) for v in p["c"]], float(self.dt),
                 float(self.params["theta"]))
-        if getattr(self, "_pushed", None) != vals:
+        if getattr(self, "_pushed", None) != vals + (cells_key,):
             self._engine_set_params(*vals)
-            self._pushed = vals
+            if cells_key != getattr(self, "_cells_key", ()):
+                for i in range(J):
+                    self.engine.set_cell_coefficient(self._net_sub(i) - 1, dg0[i].values if i in dg0 else None)
+                self._cells_key = cells_key
+            self._pushed = vals + (cells_key,)
             self._pc_dirty = True
         return J
 
@@ -150,9 +162,54 @@ class MPETSolver(object):
         self._push_params()
         key = self._pushed
         if self._prec_assembled_for != key:
+            if self.VQ.nreal and not self._border_ready:
+                self._set_prec_shifts()
             self.engine.assemble_prec()
             self._prec_assembled_for = key
             self._pc_dirty = True
+        if self.VQ.nreal and not self._border_ready:
+            self._setup_border()
+
+    # ------------------------------------------------------------------ nullspaces (mpetsolver.py:203-215)
+    def _set_prec_shifts(self):
+        """Mass shifts that make the preconditioner blocks of the constrained fields definite: the reference's
+        (commented-out) ``inner(u, v)*dx`` (mpetsolver.py:276-277) and ``p[k]*q[k]*dx`` (:274), scaled with the
+        block's own stiffness coefficient over the squared domain diameter."""
+        x = self.problem.mesh.coordinates
+        diam2 = float(np.sum((x.max(axis=0) - x.min(axis=0)) ** 2))
+        p = self.problem.params
+        mu, _ = convert_to_mu_lmbda(float(p["E"]), float(p["nu"]))
+        dth = float(self.dt) * float(self.params["theta"])
+        nf = self._num_p1_fields()
+        shift_p = [0.0] * nf
+        for i, flag in enumerate(self.problem.p_has_nullspace):
+            if flag:
+                shift_p[self._net_sub(i) - 1] = 10.0 * dth * float(p["K"][i]) / diam2
+        self.engine.set_prec_shift(10.0 * mu / diam2 if self.problem.u_has_nullspace else 0.0, shift_p)
+
+    def _setup_border(self):
+        """Columns of the Lagrange-multiplier border: c_i = int Z_i . v dx for the rigid motions Z_i
+        (rm_basis_L2.py), c_k = int q_i dx for a pressure with nullspace."""
+        from .rm_basis_L2 import rigid_motions
+        sp, eng = self.VQ, self.engine
+        C = torch.zeros((sp.nreal, sp.N), dtype=torch.float64, device=eng.device)
+        r = 0
+        if self.problem.u_has_nullspace:
+            x2 = sp.node2_coordinates()
+            for Z in rigid_motions(self.problem.mesh):
+                z = np.asarray(Z(x2), dtype=float)
+                for k in range(3):
+                    zk = torch.as_tensor(np.ascontiguousarray(z[:, k]), device=eng.device)
+                    eng.mass_apply(2, 1.0, zk, C[r, k * sp.N2:(k + 1) * sp.N2])
+                r += 1
+        for i, flag in enumerate(self.problem.p_has_nullspace):
+            if flag:
+                lo, hi = sp.sub_range(self._net_sub(i))
+                C[r, lo:hi] = self._lumped_vec(1)
+                r += 1
+        eng.set_border(C)
+        self._border_ready = True
+        self._pc_dirty = True
 
     def _sync_dirichlet(self, bcs):
         """Constrained dof set -> engine (only when it changed)."""
@@ -263,7 +320,7 @@ class MPETSolver(object):
             return Matrix(self, "P")
         if kind == "a_robin":
             return self._robin_entries(form.index)
-        b = torch.zeros(sp.N, dtype=torch.float64, device=eng.device)
+        b = torch.zeros(sp.N + sp.nreal, dtype=torch.float64, device=eng.device)
         if kind == "L":
             eng.rhs_prev(self.up_.x, b)
         elif kind == "L1":
