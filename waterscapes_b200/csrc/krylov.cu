@@ -27,12 +27,13 @@ namespace {
 const int kRedBlocks = 1184;   // 148 SMs x 8
 const int kBorderPad = 16;     // entries appended to every Krylov vector when multipliers border the system
 const int kRedThreads = 256;
+const int kGmresMaxRestart = 120, kGmresLd = kGmresMaxRestart + 1;
 
 enum {
     S_BETA = 0, S_BETA_OLD, S_ETA, S_C, S_C_OLD, S_S, S_S_OLD, S_ALPHA, S_RHO1, S_RHO2, S_RHO3, S_CETA,
-    S_NORM, S_NORM0, S_TOL, S_DP, S_BNORM, S_STAG_REF, S_BTRUE, S_COUNT = 32
+    S_NORM, S_NORM0, S_TOL, S_DP, S_BNORM, S_STAG_REF, S_BTRUE, S_INV, S_COUNT = 32
 };
-enum { F_DONE = 0, F_CONV, F_ITERS, F_MAXIT, F_BREAKDOWN, F_PENDING, F_STAG, F_COUNT = 8 };
+enum { F_DONE = 0, F_CONV, F_ITERS, F_MAXIT, F_BREAKDOWN, F_PENDING, F_STAG, F_JCOUNT, F_COUNT = 8 };
 // stagnation exit: less than 1 % reduction of the (monotone) MINRES residual norm over kStagWindow iterations
 const int kStagWindow = 256;
 const double kStagFactor = 0.99;
@@ -275,9 +276,102 @@ __global__ void k_multi_axpy(const double* __restrict__ V, int64_t ldv, int nv, 
     w[i] = acc;
 }
 
-__global__ void k_scale_copy(const double* __restrict__ src, double scale, int64_t n, double* __restrict__ dst) {
+// dst = src * (*scale), scale on the device (1 / ||.|| of the vector being normalised)
+__global__ void k_scale_copy(const double* __restrict__ src, const double* __restrict__ scale, int64_t n,
+                             double* __restrict__ dst, const int* __restrict__ done) {
+    if (done && *done) return;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i] * scale;
+    if (i < n) dst[i] = src[i] * *scale;
+}
+
+// x += sum_{k < *count} y[k] V[k]   (end of a GMRES cycle; the column count of the cycle lives on the device)
+__global__ void k_multi_axpy_count(const double* __restrict__ V, int64_t ldv, const int* __restrict__ count,
+                                   const double* __restrict__ y, int64_t n, double* __restrict__ x) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nv = *count;
+    double acc = x[i];
+    for (int k = 0; k < nv; ++k) acc += y[k] * V[k * ldv + i];
+    x[i] = acc;
+}
+
+// GMRES scalar recurrences on the device (one thread; the Hessenberg matrix has at most 120 columns), so that
+// the host only polls the flags every few iterations, like MINRES.
+__global__ void k_gmres_init(const double* __restrict__ red, int maxit, double* __restrict__ sc, int* __restrict__ fl) {
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < S_COUNT; ++i) sc[i] = 0.0;
+    for (int i = 0; i < F_COUNT; ++i) fl[i] = 0;
+    sc[S_BNORM] = sqrt(fmax(red[0], 0.0));        // ||B b||_2: PETSc's default reference norm (left preconditioning)
+    sc[S_NORM0] = -1.0;
+    fl[F_MAXIT] = maxit;
+}
+
+// start of a cycle: beta = ||B r||_2 (red[0] = its square); g = beta e_0
+__global__ void k_gmres_begin(const double* __restrict__ red, double rtol, double atol, int norm_mode, int m,
+                              double* __restrict__ sc, int* __restrict__ fl, double* __restrict__ g) {
+    if (threadIdx.x != 0 || fl[F_DONE]) return;
+    const double beta = sqrt(fmax(red[0], 0.0));
+    if (sc[S_NORM0] < 0.0) {
+        sc[S_NORM0] = beta;
+        double bn = sc[S_BNORM];
+        if (!(bn > 0.0)) bn = beta;
+        sc[S_BTRUE] = bn;
+        if (norm_mode == 1) bn = fmin(bn, beta);
+        sc[S_BNORM] = bn;
+        sc[S_TOL] = fmax(rtol * bn, atol);
+    }
+    sc[S_NORM] = beta;
+    fl[F_JCOUNT] = 0;
+    if (beta <= sc[S_TOL] || beta == 0.0) { fl[F_CONV] = 1; fl[F_DONE] = 1; return; }
+    if (fl[F_ITERS] >= fl[F_MAXIT]) { fl[F_DONE] = 1; return; }
+    g[0] = beta;
+    for (int i = 1; i <= m; ++i) g[i] = 0.0;
+    sc[S_INV] = 1.0 / beta;
+}
+
+// column j of the Hessenberg matrix: h = h1 + h2 (the two Gram-Schmidt passes), h[j+1] = ||w|| (red[0] = its
+// square); previous Givens rotations, the new one, the residual norm estimate |g[j+1]| and the convergence test.
+// R (upper triangular after the rotations) is column-major with leading dimension ldh.
+__global__ void k_gmres_rotate(int j, int ldh, const double* __restrict__ h1, const double* __restrict__ h2,
+                               const double* __restrict__ red, double* __restrict__ R, double* __restrict__ cs,
+                               double* __restrict__ sn, double* __restrict__ g, double* __restrict__ sc,
+                               int* __restrict__ fl) {
+    if (threadIdx.x != 0 || fl[F_DONE]) return;
+    double* col = R + (int64_t)j * ldh;
+    for (int i = 0; i <= j; ++i) col[i] = h1[i] + h2[i];
+    const double hn = sqrt(fmax(red[0], 0.0));
+    double below = hn;
+    for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * col[i] + sn[i] * col[i + 1];
+        col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+        col[i] = t;
+    }
+    const double den = hypot(col[j], below);
+    cs[j] = den > 0.0 ? col[j] / den : 1.0;
+    sn[j] = den > 0.0 ? below / den : 0.0;
+    col[j] = den;
+    g[j + 1] = -sn[j] * g[j];
+    g[j] = cs[j] * g[j];
+    fl[F_ITERS] += 1;
+    fl[F_JCOUNT] = j + 1;
+    const double norm = fabs(g[j + 1]);
+    sc[S_NORM] = norm;
+    sc[S_INV] = hn > 0.0 ? 1.0 / hn : 0.0;
+    if (norm <= sc[S_TOL]) { fl[F_CONV] = 1; fl[F_DONE] = 1; }
+    else if (hn == 0.0) { fl[F_BREAKDOWN] = 1; fl[F_DONE] = 1; }
+    else if (fl[F_ITERS] >= fl[F_MAXIT]) fl[F_DONE] = 1;
+}
+
+// end of a cycle: back substitution R y = g over the columns completed in this cycle
+__global__ void k_gmres_solve(int ldh, const double* __restrict__ R, const double* __restrict__ g,
+                              const int* __restrict__ fl, double* __restrict__ y) {
+    if (threadIdx.x != 0) return;
+    const int jj = fl[F_JCOUNT];
+    for (int i = jj - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int q = i + 1; q < jj; ++q) s -= R[(int64_t)q * ldh + i] * y[q];
+        y[i] = s / R[(int64_t)i * ldh + i];
+    }
 }
 
 // ---------------------------------------------------------------------------------- bordered system (multipliers)
@@ -344,6 +438,7 @@ struct KrylovWork {
     double* basis = nullptr;   // GMRES: (restart + 1) vectors
     int basis_m = 0;
     double* hdev = nullptr;
+    double* gm = nullptr;      // GMRES: R (121 x 120, column-major), then cs, sn, g (128 each)
     double* h_sc = nullptr;    // pinned mirrors
     int* h_fl = nullptr;
     // CUDA graphs of the MINRES iteration body: [0..3] its four segments (SpMV | halo + dot | preconditioner |
@@ -387,6 +482,7 @@ static KrylovWork* get_work(mpet_ctx* ctx) {
     k->red = dev_alloc<double>(ctx, 8);
     k->fl = dev_alloc<int>(ctx, F_COUNT);
     k->hdev = dev_alloc<double>(ctx, 256);
+    k->gm = dev_alloc<double>(ctx, kGmresLd * kGmresMaxRestart + 3 * 128);
     CUDA_CHECK(cudaMallocHost(&k->h_sc, sizeof(double) * S_COUNT));
     CUDA_CHECK(cudaMallocHost(&k->h_fl, sizeof(int) * F_COUNT));
     ctx->kw = k;
@@ -727,10 +823,14 @@ static void multidot(mpet_ctx* ctx, KrylovWork* k, const double* V, int64_t ldv,
 }
 
 static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {
+    // Left-preconditioned GMRES(m), classical Gram-Schmidt in two passes (CGS2).  Everything scalar -- Hessenberg
+    // column, Givens rotations, residual estimate, convergence / iteration-limit test, the triangular solve at the
+    // end of a cycle -- runs in single-thread kernels on the device; once the DONE flag is up all queued kernels
+    // return immediately and the host polls the flags every few iterations, like MINRES.
     KrylovWork* k = get_work(ctx);
     const int64_t n = k->n;
     const int m = ctx->restart;
-    MPET_REQUIRE(m >= 1 && m <= 120, "GMRES restart must be in 1..120");
+    MPET_REQUIRE(m >= 1 && m <= kGmresMaxRestart, "GMRES restart must be in 1..120");
     const int64_t ldv = (n + 3) & ~(int64_t)3;   // 32-byte aligned basis vectors (256-bit loads in block_spmv)
     if (k->basis_m < m) {
         k->basis = dev_alloc<double>(ctx, (int64_t)(m + 1) * ldv);
@@ -738,110 +838,78 @@ static void gmres(mpet_ctx* ctx, const double* b, double* x, double* info, cudaS
     }
     const uint8_t* mask = ctx->n_bc > 0 ? ctx->bc_mask_int : nullptr;
     double* V = k->basis;
+    double *R = k->gm, *cs = k->gm + (int64_t)kGmresLd * kGmresMaxRestart, *sn = cs + 128, *g = sn + 128;
+    const int* done = k->fl + F_DONE;
+    const int gridn = grid_for(n, 256);
     CUDA_CHECK(cudaMemsetAsync(k->u_old, 0, sizeof(double) * k->n, st));
     border_setup(ctx, k, st);
     load_system(ctx, k, b, x, st);
-    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
-    int iters = 0;
-    bool converged = false;
-    double norm0 = -1, norm = 0, tol = 0, bnorm = 0, btrue = 0;
-    {   // PETSc default with a nonzero initial guess: tolerance relative to ||B b||_2 (left preconditioning)
-        eliminated_rhs(ctx, k, st);
-        pc_apply_dist(ctx, k->r, k->z, nullptr, st);
-        dot_to(ctx, k, k->z, k->z, nullptr, st);
-        CUDA_CHECK(cudaMemcpyAsync(&bnorm, k->red, sizeof(double), cudaMemcpyDeviceToHost, st));
+    // PETSc default with a nonzero initial guess: tolerance relative to ||B b||_2 (left preconditioning)
+    eliminated_rhs(ctx, k, st);
+    pc_apply_dist(ctx, k->r, k->z, nullptr, st);
+    dot_to(ctx, k, k->z, k->z, nullptr, st);
+    k_gmres_init<<<1, 32, 0, st>>>(k->red, ctx->maxit, k->sc, k->fl);
+    LAUNCH_CHECK(ctx);
+    auto poll = [&]() {
+        CUDA_CHECK(cudaMemcpyAsync(k->h_fl, k->fl, sizeof(int) * F_COUNT, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(k->h_sc, k->sc, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
-        bnorm = std::sqrt(bnorm);
-    }
-    while (!converged && iters < ctx->maxit) {
+        return k->h_fl[F_DONE] != 0;
+    };
+    const int check_every = 5;
+    int enq = 0;
+    while (true) {
         initial_residual(ctx, k, st);
         pc_apply_dist(ctx, k->r, k->z, nullptr, st);
         dot_to(ctx, k, k->z, k->z, nullptr, st);          // k->red[0]: summed over owned dofs and all ranks
-        double bb = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&bb, k->red, sizeof(double), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
-        double beta = std::sqrt(bb);
-        if (norm0 < 0) {
-            norm0 = beta;
-            if (!(bnorm > 0.0)) bnorm = beta;
-            btrue = bnorm;
-            if (ctx->norm_mode == 1) bnorm = std::min(bnorm, beta);
-            tol = std::max(ctx->rtol * bnorm, ctx->atol);
-        }
-        norm = beta;
-        if (beta <= tol || beta == 0.0) { converged = true; break; }
-        k_scale_copy<<<grid_for(n, 256), 256, 0, st>>>(k->z, 1.0 / beta, n, V);
+        k_gmres_begin<<<1, 32, 0, st>>>(k->red, ctx->rtol, ctx->atol, ctx->norm_mode, m, k->sc, k->fl, g);
         LAUNCH_CHECK(ctx);
-        std::fill(g.begin(), g.end(), 0.0);
-        g[0] = beta;
-        int j = 0;
-        for (; j < m && iters < ctx->maxit; ++j) {
+        if (poll()) break;                                // converged (or out of iterations) at the start of a cycle
+        k_scale_copy<<<gridn, 256, 0, st>>>(k->z, k->sc + S_INV, n, V, done);
+        LAUNCH_CHECK(ctx);
+        bool stop = false;
+        for (int j = 0; j < m && enq < ctx->maxit && !stop; ++j) {
             double* w = V + (int64_t)(j + 1) * ldv;
-            apply_operator(ctx, k, V + (int64_t)j * ldv, k->r, mask, nullptr, st);
-            dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, nullptr, st);      // ghost rows of the local matrix are incomplete
-            pc_apply_dist(ctx, k->r, w, nullptr, st);
-            // classical Gram-Schmidt, two passes (CGS2)
+            cudaEvent_t pe = prof_begin(ctx, st);
+            apply_operator(ctx, k, V + (int64_t)j * ldv, k->r, mask, done, st);
+            prof_end(ctx, PROF_SPMV, pe, st);
+            dist_halo(ctx, DIST_PLAN_KRYLOV, k->r, false, done, st);      // ghost rows of the local matrix are incomplete
+            pe = prof_begin(ctx, st);
+            pc_apply_dist(ctx, k->r, w, done, st);
+            prof_end(ctx, PROF_PC, pe, st);
             multidot(ctx, k, V, ldv, j + 1, w, k->hdev, 0, st);
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev, -1.0, n, w);
+            k_multi_axpy<<<gridn, 256, 0, st>>>(V, ldv, j + 1, k->hdev, -1.0, n, w);
             LAUNCH_CHECK(ctx);
             multidot(ctx, k, V, ldv, j + 1, w, k->hdev + 128, 0, st);
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, j + 1, k->hdev + 128, -1.0, n, w);
+            k_multi_axpy<<<gridn, 256, 0, st>>>(V, ldv, j + 1, k->hdev + 128, -1.0, n, w);
             LAUNCH_CHECK(ctx);
             dot_to(ctx, k, w, w, nullptr, st);
-            CUDA_CHECK(cudaMemcpyAsync(k->hdev + j + 1, k->red, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            std::vector<double> h1(j + 2), h2(j + 1);
-            CUDA_CHECK(cudaMemcpyAsync(h1.data(), k->hdev, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaMemcpyAsync(h2.data(), k->hdev + 128, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            for (int i = 0; i <= j; ++i) hcol[i] = h1[i] + h2[i];
-            double hn = std::sqrt(std::max(0.0, h1[j + 1]));
-            hcol[j + 1] = hn;
-            if (hn > 0) {
-                k_scale_copy<<<grid_for(n, 256), 256, 0, st>>>(w, 1.0 / hn, n, w);
-                LAUNCH_CHECK(ctx);
-            }
-            for (int i = 0; i < j; ++i) {   // previous rotations
-                double t = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
-                hcol[i + 1] = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
-                hcol[i] = t;
-            }
-            double den = std::hypot(hcol[j], hcol[j + 1]);
-            cs[j] = den > 0 ? hcol[j] / den : 1.0;
-            sn[j] = den > 0 ? hcol[j + 1] / den : 0.0;
-            hcol[j] = den;
-            g[j + 1] = -sn[j] * g[j];
-            g[j] = cs[j] * g[j];
-            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
-            ++iters;
-            norm = std::fabs(g[j + 1]);
-            if (norm <= tol || hn == 0.0) { converged = norm <= tol; ++j; break; }
-        }
-        // solve the triangular system and update x
-        int jj = j;
-        for (int i = jj - 1; i >= 0; --i) {
-            double s = g[i];
-            for (int q = i + 1; q < jj; ++q) s -= H[(size_t)i * m + q] * y[q];
-            y[i] = s / H[(size_t)i * m + i];
-        }
-        if (jj > 0) {
-            CUDA_CHECK(cudaMemcpyAsync(k->hdev, y.data(), sizeof(double) * jj, cudaMemcpyHostToDevice, st));
-            k_multi_axpy<<<grid_for(n, 256), 256, 0, st>>>(V, ldv, jj, k->hdev, 1.0, n, k->xi);
+            k_gmres_rotate<<<1, 32, 0, st>>>(j, kGmresLd, k->hdev, k->hdev + 128, k->red, R, cs, sn, g, k->sc, k->fl);
             LAUNCH_CHECK(ctx);
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            k_scale_copy<<<gridn, 256, 0, st>>>(w, k->sc + S_INV, n, w, done);
+            LAUNCH_CHECK(ctx);
+            ++enq;
+            if ((j + 1) % check_every == 0 || j + 1 == m || enq >= ctx->maxit) stop = poll();
         }
-        if (jj == 0) break;
+        // x += V y with R y = g over the columns this cycle completed (count on the device)
+        k_gmres_solve<<<1, 32, 0, st>>>(kGmresLd, R, g, k->fl, k->hdev);
+        LAUNCH_CHECK(ctx);
+        k_multi_axpy_count<<<gridn, 256, 0, st>>>(V, ldv, k->fl + F_JCOUNT, k->hdev, n, k->xi);
+        LAUNCH_CHECK(ctx);
+        if (stop || enq >= ctx->maxit) break;
     }
     store_solution(ctx, k, x, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    poll();
     dist_check(ctx);
-    info[0] = iters;
-    info[1] = converged ? 1.0 : 0.0;
-    info[2] = bnorm > 0 ? norm / bnorm : 0.0;
-    info[3] = norm0 < 0 ? 0.0 : norm0;
-    info[4] = 0.0;
-    info[5] = converged ? 2.0 : -3.0;
-    info[6] = bnorm;
-    info[7] = btrue;
+    prof_collect(ctx);
+    info[0] = (double)k->h_fl[F_ITERS];
+    info[1] = (double)k->h_fl[F_CONV];
+    info[2] = k->h_sc[S_BNORM] > 0 ? k->h_sc[S_NORM] / k->h_sc[S_BNORM] : 0.0;
+    info[3] = k->h_sc[S_NORM0] < 0 ? 0.0 : k->h_sc[S_NORM0];
+    info[4] = (double)k->h_fl[F_BREAKDOWN];
+    info[5] = k->h_fl[F_CONV] ? 2.0 : (k->h_fl[F_BREAKDOWN] ? -4.0 : -3.0);
+    info[6] = k->h_sc[S_BNORM];
+    info[7] = k->h_sc[S_BTRUE];
 }
 
 void krylov_solve(mpet_ctx* ctx, const double* b, double* x, double* info, cudaStream_t st) {

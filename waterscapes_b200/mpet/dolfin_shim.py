@@ -64,7 +64,9 @@ class Mesh:
             nv = self.num_vertices()
             tri = np.stack([c[:, [1, 2, 3]], c[:, [0, 2, 3]], c[:, [0, 1, 3]], c[:, [0, 1, 2]]], axis=1)
             flat = tri.reshape(-1, 3)
-            key = (flat[:, 0] * nv + flat[:, 1]) * nv + flat[:, 2]
+            # two-stage key (pair id, third vertex): an nv^3 product overflows int64 beyond ~2.09 M vertices
+            _, pid = np.unique(flat[:, 0] * nv + flat[:, 1], return_inverse=True)
+            key = pid.astype(np.int64).ravel() * nv + flat[:, 2]
             order = np.argsort(key, kind="stable")
             ks = key[order]
             single = np.ones(ks.shape[0], dtype=bool)
