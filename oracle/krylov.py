@@ -22,9 +22,9 @@ CHEB_DEGREE = 2
 CHEB_RATIO = 4.0
 # well-conditioned blocks (cond(D^-1 A) <= POLY_KAPPA_MAX, e.g. the mass-dominated network blocks) are inverted
 # by a Chebyshev polynomial on the WHOLE spectrum instead of a V-cycle (amg.cu: same constants)
-POLY_KAPPA_MAX = 12.0
+POLY_KAPPA_MAX = 32.0
 POLY_TARGET = 1.0e-4
-POLY_MAX_DEGREE = 16
+POLY_MAX_DEGREE = 28
 LANCZOS_STEPS = 40
 # Galerkin operators of the aggregated levels: entries below DROP_TOL * sqrt(a_ii a_jj) are lumped into the
 # diagonal (smoothed aggregation fills in quickly: 850 entries per row two levels below the mesh on cfg5)

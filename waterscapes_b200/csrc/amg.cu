@@ -556,10 +556,15 @@ HostCsr drop_small(const HostCsr& A, double tol) {
 const int kChebDegree = 2;
 // well-conditioned blocks (cond(D^-1 A) <= kPolyKappaMax, e.g. mass-dominated network blocks) are inverted by a
 // Chebyshev polynomial on the WHOLE spectrum instead of a V-cycle (oracle/krylov.py: same constants)
-const double kPolyKappaMax = 12.0;
+// Threshold: a degree-k polynomial costs k passes over the P1 matrix and no coarse levels / all-gathers; up to
+// cond ~ 32 (degree <= 28 for the 1e-4 target) that is no more than the 2-3 strong cycles of degree 4 it replaces.
+// It was 12 until the 8-GPU weak-scaling run (144^3 cubes): h had shrunk enough for the second network of cfg5 to
+// cross 12 (spectrum [0.136, 1.91]), its block fell back to ONE light V-cycle and MINRES needed 154-181 iterations
+// instead of 58-67 (profiles/r02_multi_gpu.md).
+const double kPolyKappaMax = 32.0;
 const double kPolyTarget = 1.0e-4;
 const double kPolyTargetLight = 1.0e-4;    // light mode (loose tolerances): residual-polynomial target of the polynomial fields
-const int kPolyMaxDegree = 16;
+const int kPolyMaxDegree = 28;
 const int kLanczosSteps = 40;
 // Galerkin operators of the aggregated levels: entries below kDropTol * sqrt(a_ii a_jj) are lumped into the diagonal.
 // Smoothed aggregation fills in quickly (cfg5: 851 entries per row two levels below the mesh, more entries than the
@@ -1246,7 +1251,8 @@ void amg_setup(mpet_ctx* ctx, cudaStream_t st) {
         double lmin = 0, lmax = 0;
         lanczos_bounds(ctx, H->levels[0], own_dev, lmin, lmax, st);
         const double lo = 0.97 * lmin, hi = 1.02 * lmax;
-        if (lmin > 0 && hi / lo <= kPolyKappaMax && !getenv("MPET_NO_POLY")) {
+        static const double kappa_max = []() { const char* e = getenv("MPET_POLY_KAPPA_MAX"); return e ? atof(e) : kPolyKappaMax; }();
+        if (lmin > 0 && hi / lo <= kappa_max && !getenv("MPET_NO_POLY")) {
             H->poly_degree = poly_degree_for(lo, hi);
             static const double light_target = []() { const char* e = getenv("MPET_POLY_TARGET_LIGHT"); return e ? atof(e) : kPolyTargetLight; }();
             H->poly_degree_light = poly_degree_for(lo, hi, light_target);
