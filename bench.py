@@ -608,7 +608,7 @@ def main():
                 "avg_launch_ms": spmv_ms, "launches_timed": prof["spmv"]["count"],
                 "traffic": traffic.get("dram_bytes_per_launch") if world == 1 and n == traffic.get("n") else None,
                 "traffic_source": traffic.get("source") if world == 1 and n == traffic.get("n") else None,
-                "preconditioner": {"kernel": "one block-diagonal AMG application (k_spmm_pipe / k_spmm_x16 passes over all levels, amg.cu)",
+                "preconditioner": {"kernel": "one block-diagonal AMG application (k_spmm_pipe / k_cheb_first / k_dense_apply passes over all levels, amg.cu)",
                                    "algorithmic_bytes_per_application": pc_bytes, "avg_application_ms": pc_ms,
                                    "achieved": pc_bytes / (pc_ms * 1e-3) / 1e9 if pc_ms > 0 else 0.0,
                                    "frac": pc_bytes / (pc_ms * 1e-3) / 1e9 / peak if pc_ms > 0 else 0.0,
