@@ -74,6 +74,21 @@ int mpet_set_params_total_pressure(mpet_ctx* ctx, double E, double nu, const dou
  * NULL to return to the constant.  Assemble (lhs and prec) again afterwards. */
 int mpet_set_cell_coefficient(mpet_ctx* ctx, int field, const double* values_dev, void* stream);
 
+/* ---- external dof numbering (`mpet_dofmap(ctx, perm*)`) ---------------------------------------
+ * DOLFIN re-orders the dofs of its FunctionSpace (parameters["reorder_dofs_serial"], SCOTCH/Boost: not reproducible
+ * outside DOLFIN), so `up.vector()` of mpetsolver.py:131-132 is not in the UFC numbering this library's contract
+ * uses.  ext_of_contract_dev i32[N] (device, copied): entry c = the CALLER's index of contract dof c -- for DOLFIN
+ * built once from `V.sub(k).dofmap().dofs()` / `vertex_to_dof_map(V.sub(3+i).collapse())` and the edge table of
+ * mpet_get_edges.  Must be a bijection of 0..N-1 (checked).  NULL returns to the contract numbering.
+ * Afterwards every dof VECTOR crossing the boundary is in the caller's numbering -- b and x of mpet_solve (the nb
+ * multipliers of a bordered system stay behind the N dofs), up_prev and b of mpet_rhs_prev, x and y of mpet_spmv,
+ * b of mpet_apply_dirichlet_rhs, r and z of mpet_pc_apply, the columns of mpet_set_border -- and so is every dof
+ * INDEX: mpet_set_dirichlet_dofs, rows / cols of mpet_add_entries.  The exports that describe the matrix itself
+ * (mpet_get_cell_dofs, mpet_get_pattern, mpet_get_values) stay in the contract numbering; the node vectors of
+ * mpet_mass_apply / mpet_lumped are per scalar space and unaffected.  Cost: one gather and one scatter of N doubles
+ * per vector argument (0.05 ms at 10 M dofs). */
+int mpet_set_dof_permutation(mpet_ctx* ctx, const int32_t* ext_of_contract_dev, void* stream);
+
 /* ---- matrix assembly ---------------------------------------------------------------------------
  * mpet_assemble_lhs  : A = assemble(a)                       (mpetsolver.py:335,412,496; form :196-201,260)
  * mpet_add_entries   : A.axpy(1.0, assemble(a_robin[i]))     (mpetsolver.py:336-338; form :252-253)

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "mpet_set_params_total_pressure": (_int, [_c_ctx, _f64, _f64, C.POINTER(_f64), C.POINTER(_f64), C.POINTER(_f64),
                                               C.POINTER(_f64), _f64, _f64]),
     "mpet_set_cell_coefficient": (_int, [_c_ctx, _int, _p, _p]),
+    "mpet_set_dof_permutation": (_int, [_c_ctx, _p, _p]),
     "mpet_assemble_lhs": (_int, [_c_ctx, _p]),
     "mpet_add_entries": (_int, [_c_ctx, _p, _p, _p, _i64, _p]),
     "mpet_assemble_prec": (_int, [_c_ctx, _p]),

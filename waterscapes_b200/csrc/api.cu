@@ -39,7 +39,73 @@ __global__ void k_cell_dofs(const int32_t* __restrict__ cell_nodes, int64_t nc, 
         out[i] = (int32_t)(3 * n2 + n * nv + cell_nodes[c * 10 + m]);
     }
 }
+
+// ---- external dof numbering (mpet_set_dof_permutation)
+__global__ void k_perm_gather(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ ext,
+                              double* __restrict__ con) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) con[i] = ext[perm[i]];
+}
+__global__ void k_perm_scatter(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ con,
+                               double* __restrict__ ext) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) ext[perm[i]] = con[i];
+}
+__global__ void k_perm_invert(int64_t n, const int32_t* __restrict__ perm, int32_t* __restrict__ inv, int* __restrict__ bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t e = perm[i];
+    if (e < 0 || e >= n) { atomicAdd(bad, 1); return; }
+    inv[e] = (int32_t)i;
+}
+__global__ void k_perm_holes(int64_t n, const int32_t* __restrict__ inv, int* __restrict__ bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && inv[i] < 0) atomicAdd(bad, 1);
+}
+__global__ void k_perm_map(int64_t n, int64_t ndof, const int32_t* __restrict__ inv, const int32_t* __restrict__ in,
+                           int32_t* __restrict__ out, int* __restrict__ bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t e = in[i];
+    if (e < 0 || e >= ndof) { atomicAdd(bad, 1); out[i] = 0; return; }
+    out[i] = inv[e];
+}
 }  // namespace
+
+// caller's vector (external numbering, `tail` extra entries behind the N dofs pass through) -> contract numbering
+static const double* to_contract(mpet_ctx* ctx, const double* ext, double* scratch, int64_t tail, cudaStream_t st) {
+    if (!ctx->perm) return ext;
+    k_perm_gather<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N, ctx->perm, ext, scratch);
+    LAUNCH_CHECK(ctx);
+    if (tail > 0)
+        CUDA_CHECK(cudaMemcpyAsync(scratch + ctx->N, ext + ctx->N, sizeof(double) * tail, cudaMemcpyDeviceToDevice, st));
+    return scratch;
+}
+static void from_contract(mpet_ctx* ctx, const double* con, double* ext, int64_t tail, cudaStream_t st) {
+    if (!ctx->perm) return;
+    k_perm_scatter<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N, ctx->perm, con, ext);
+    LAUNCH_CHECK(ctx);
+    if (tail > 0)
+        CUDA_CHECK(cudaMemcpyAsync(ext + ctx->N, con + ctx->N, sizeof(double) * tail, cudaMemcpyDeviceToDevice, st));
+}
+// caller's dof indices -> contract indices (temporary device array, freed by the caller after a stream sync)
+static int32_t* map_dofs(mpet_ctx* ctx, const int32_t* ext, int64_t n, cudaStream_t st) {
+    int32_t* out = nullptr;
+    int* bad = nullptr;
+    CUDA_CHECK(cudaMalloc(&out, sizeof(int32_t) * std::max<int64_t>(n, 1)));
+    CUDA_CHECK(cudaMalloc(&bad, sizeof(int)));
+    CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    if (n > 0) {
+        k_perm_map<<<grid_for(n, 256), 256, 0, st>>>(n, ctx->N, ctx->perm_inv, ext, out, bad);
+        LAUNCH_CHECK(ctx);
+    }
+    int hbad = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(bad);
+    if (hbad) { cudaFree(out); throw MpetError("dof index outside 0..N-1"); }
+    return out;
+}
 
 static cudaEvent_t prof_event(mpet_ctx* ctx) {
     if (!ctx->prof.pool.empty()) {
@@ -299,6 +365,44 @@ int mpet_set_cell_coefficient(mpet_ctx* ctx, int field, const double* values_dev
     MPET_CATCH(ctx)
 }
 
+int mpet_set_dof_permutation(mpet_ctx* ctx, const int32_t* ext_of_contract_dev, void* stream) {
+    MPET_TRY(ctx)
+    MPET_REQUIRE(ctx->N > 0, "mpet_set_mesh must be called first");
+    cudaStream_t st = as_stream(stream);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (ctx->perm) {
+        dev_free(ctx, ctx->perm); dev_free(ctx, ctx->perm_inv); dev_free(ctx, ctx->perm_a); dev_free(ctx, ctx->perm_b);
+        ctx->perm = ctx->perm_inv = nullptr;
+        ctx->perm_a = ctx->perm_b = nullptr;
+    }
+    if (ext_of_contract_dev) {
+        int32_t* perm = dev_alloc<int32_t>(ctx, ctx->N);
+        int32_t* inv = dev_alloc<int32_t>(ctx, ctx->N);
+        int* bad = nullptr;
+        CUDA_CHECK(cudaMalloc(&bad, sizeof(int)));
+        CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+        CUDA_CHECK(cudaMemcpyAsync(perm, ext_of_contract_dev, sizeof(int32_t) * ctx->N, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(inv, 0xFF, sizeof(int32_t) * ctx->N, st));
+        k_perm_invert<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N, perm, inv, bad);
+        LAUNCH_CHECK(ctx);
+        k_perm_holes<<<grid_for(ctx->N, 256), 256, 0, st>>>(ctx->N, inv, bad);
+        LAUNCH_CHECK(ctx);
+        int hbad = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(bad);
+        if (hbad) {
+            dev_free(ctx, perm); dev_free(ctx, inv);
+            MPET_REQUIRE(false, "the dof permutation is not a bijection of 0..N-1");
+        }
+        ctx->perm = perm;
+        ctx->perm_inv = inv;
+        ctx->perm_a = dev_alloc<double>(ctx, ctx->N + 16);
+        ctx->perm_b = dev_alloc<double>(ctx, ctx->N + 16);
+    }
+    MPET_CATCH(ctx)
+}
+
 int mpet_assemble_lhs(mpet_ctx* ctx, void* stream) {
     MPET_TRY(ctx)
     cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
@@ -310,7 +414,16 @@ int mpet_assemble_lhs(mpet_ctx* ctx, void* stream) {
 int mpet_add_entries(mpet_ctx* ctx, const int32_t* rows, const int32_t* cols, const double* vals,
                      int64_t n, void* stream) {
     MPET_TRY(ctx)
-    add_entries(ctx, rows, cols, vals, n, as_stream(stream));
+    if (ctx->perm) {
+        int32_t* r = map_dofs(ctx, rows, n, as_stream(stream));
+        int32_t* c = nullptr;
+        try { c = map_dofs(ctx, cols, n, as_stream(stream)); } catch (...) { cudaFree(r); throw; }
+        try { add_entries(ctx, r, c, vals, n, as_stream(stream)); CUDA_CHECK(cudaStreamSynchronize(as_stream(stream))); }
+        catch (...) { cudaFree(r); cudaFree(c); throw; }
+        cudaFree(r); cudaFree(c);
+    } else {
+        add_entries(ctx, rows, cols, vals, n, as_stream(stream));
+    }
     MPET_CATCH(ctx)
 }
 
@@ -330,7 +443,14 @@ int mpet_get_values(mpet_ctx* ctx, int which, double* vals, void* stream) {
 int mpet_set_dirichlet_dofs(mpet_ctx* ctx, const int32_t* dofs, int64_t n, void* stream) {
     MPET_TRY(ctx)
     MPET_REQUIRE(ctx->N > 0, "mpet_set_mesh must be called first");
-    set_dirichlet_dofs(ctx, dofs, n, as_stream(stream));
+    if (ctx->perm) {
+        int32_t* d = map_dofs(ctx, dofs, n, as_stream(stream));
+        try { set_dirichlet_dofs(ctx, d, n, as_stream(stream)); CUDA_CHECK(cudaStreamSynchronize(as_stream(stream))); }
+        catch (...) { cudaFree(d); throw; }
+        cudaFree(d);
+    } else {
+        set_dirichlet_dofs(ctx, dofs, n, as_stream(stream));
+    }
     MPET_CATCH(ctx)
 }
 
@@ -345,7 +465,14 @@ int mpet_set_dirichlet_values(mpet_ctx* ctx, const double* vals, void* stream) {
 int mpet_rhs_prev(mpet_ctx* ctx, const double* up_prev, double* b, void* stream) {
     MPET_TRY(ctx)
     cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
-    rhs_prev(ctx, up_prev, b, as_stream(stream));
+    if (ctx->perm) {
+        const double* up_c = to_contract(ctx, up_prev, ctx->perm_a, 0, as_stream(stream));
+        to_contract(ctx, b, ctx->perm_b, 0, as_stream(stream));
+        rhs_prev(ctx, up_c, ctx->perm_b, as_stream(stream));
+        from_contract(ctx, ctx->perm_b, b, 0, as_stream(stream));
+    } else {
+        rhs_prev(ctx, up_prev, b, as_stream(stream));
+    }
     prof_end(ctx, PROF_RHS, pe, as_stream(stream));
     MPET_CATCH(ctx)
 }
@@ -387,7 +514,13 @@ int mpet_lumped(mpet_ctx* ctx, int space, double* w, void* stream) {
 
 int mpet_apply_dirichlet_rhs(mpet_ctx* ctx, double* b, void* stream) {
     MPET_TRY(ctx)
-    scatter_bc_values(ctx, b, as_stream(stream));
+    if (ctx->perm) {
+        to_contract(ctx, b, ctx->perm_a, 0, as_stream(stream));
+        scatter_bc_values(ctx, ctx->perm_a, as_stream(stream));
+        from_contract(ctx, ctx->perm_a, b, 0, as_stream(stream));
+    } else {
+        scatter_bc_values(ctx, b, as_stream(stream));
+    }
     MPET_CATCH(ctx)
 }
 
@@ -395,7 +528,12 @@ int mpet_spmv(mpet_ctx* ctx, const double* x, double* y, void* stream) {
     MPET_TRY(ctx)
     MPET_REQUIRE(ctx->lhs_ready, "mpet_assemble_lhs must run first");
     cudaEvent_t pe = prof_begin(ctx, as_stream(stream));
-    spmv_api(ctx, x, y, as_stream(stream));
+    if (ctx->perm) {
+        spmv_api(ctx, to_contract(ctx, x, ctx->perm_a, 0, as_stream(stream)), ctx->perm_b, as_stream(stream));
+        from_contract(ctx, ctx->perm_b, y, 0, as_stream(stream));
+    } else {
+        spmv_api(ctx, x, y, as_stream(stream));
+    }
     prof_end(ctx, PROF_VEC, pe, as_stream(stream));
     MPET_CATCH(ctx)
 }
@@ -439,7 +577,8 @@ int mpet_set_border(mpet_ctx* ctx, int nb, const double* columns_dev, void* stre
     if (nb > 0) {
         ctx->border = dev_alloc<double>(ctx, (int64_t)nb * ctx->Nint);
         for (int i = 0; i < nb; ++i)
-            to_internal(ctx, columns_dev + (int64_t)i * ctx->N, ctx->border + (int64_t)i * ctx->Nint, st);
+            to_internal(ctx, to_contract(ctx, columns_dev + (int64_t)i * ctx->N, ctx->perm_a, 0, st),
+                        ctx->border + (int64_t)i * ctx->Nint, st);
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
     MPET_CATCH(ctx)
@@ -461,13 +600,26 @@ int mpet_pc_setup(mpet_ctx* ctx, void* stream) {
 
 int mpet_solve(mpet_ctx* ctx, const double* b, double* x, double* info, void* stream) {
     MPET_TRY(ctx)
-    krylov_solve(ctx, b, x, info, as_stream(stream));
+    if (ctx->perm) {       // multipliers of a bordered system (behind the N dofs) pass through unpermuted
+        const double* bc = to_contract(ctx, b, ctx->perm_a, ctx->nb, as_stream(stream));
+        to_contract(ctx, x, ctx->perm_b, ctx->nb, as_stream(stream));
+        krylov_solve(ctx, bc, ctx->perm_b, info, as_stream(stream));
+        from_contract(ctx, ctx->perm_b, x, ctx->nb, as_stream(stream));
+        CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+    } else {
+        krylov_solve(ctx, b, x, info, as_stream(stream));
+    }
     MPET_CATCH(ctx)
 }
 
 int mpet_pc_apply(mpet_ctx* ctx, const double* r, double* z, void* stream) {
     MPET_TRY(ctx)
-    pc_apply(ctx, r, z, as_stream(stream));
+    if (ctx->perm) {
+        pc_apply(ctx, to_contract(ctx, r, ctx->perm_a, 0, as_stream(stream)), ctx->perm_b, as_stream(stream));
+        from_contract(ctx, ctx->perm_b, z, 0, as_stream(stream));
+    } else {
+        pc_apply(ctx, r, z, as_stream(stream));
+    }
     MPET_CATCH(ctx)
 }
 

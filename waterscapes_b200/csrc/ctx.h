@@ -174,6 +174,11 @@ struct mpet_ctx {
 
     // Lagrange multipliers bordering the system (nullspace handling)
     int nb = 0;                      // number of multipliers (<= 16)
+    // external dof numbering at the ABI (mpet_set_dof_permutation): perm[c] = caller's index of contract dof c
+    int32_t* perm = nullptr;
+    int32_t* perm_inv = nullptr;
+    double* perm_a = nullptr;        // [N + 16] scratch vectors in the contract numbering
+    double* perm_b = nullptr;
     double* border = nullptr;        // [nb][Nint] columns c_i in the solver-internal layout
     double* border_scale = nullptr;  // [16] c_i . B c_i
     bool border_scaled = false;

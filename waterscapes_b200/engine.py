@@ -106,6 +106,16 @@ class Engine:
         assert v.numel() == self.sizes["Nc"]
         self._ck(self.lib.mpet_set_cell_coefficient(self._ctx, int(field), _ptr(v), self._stream()))
 
+    def set_dof_permutation(self, ext_of_contract):
+        """Caller's dof numbering: entry c = the caller's index of contract (UFC) dof c; None = contract numbering.
+        Afterwards dof vectors and dof indices crossing the ABI are in the caller's numbering."""
+        if ext_of_contract is None:
+            self._ck(self.lib.mpet_set_dof_permutation(self._ctx, C.c_void_p(0), self._stream()))
+            return
+        perm = self._dev(ext_of_contract, torch.int32)
+        assert perm.numel() == self.sizes["N"]
+        self._ck(self.lib.mpet_set_dof_permutation(self._ctx, _ptr(perm), self._stream()))
+
     def assemble_lhs(self):
         self._ck(self.lib.mpet_assemble_lhs(self._ctx, self._stream()))
 
