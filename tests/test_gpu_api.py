@@ -242,3 +242,30 @@ def test_hdf5_mesh_and_marker_ingestion(tmp_path):
     r = H5Reader(out)
     assert np.array_equal(r.read("/up/vector_0"), up1.vector().get_local())
     assert abs(r.attrs("/u/vector_0")["timestamp"] - 0.1) < 1e-15
+
+
+@pytest.mark.parametrize("df,dg", [(3, 3), (1, 2)])
+def test_source_data_of_other_degrees_matches_oracle(df, dg):
+    """Expression(degree=d) source data with d != the test space's degree (the reference's MMS tests use d = 3,
+    test_convergence_mpetsolver.py:129-131): DOLFIN interpolates it cell-wise into P_d and integrates exactly; the GPU
+    path applies the host-built cell-lattice operator with mpet_csr_spmv.  b of one step vs the oracle <= 1e-12."""
+    from waterscapes_b200.mpet import Expression
+    n, J, theta, dt, T = 3, 2, 0.5, 0.1, 0.1
+    mesh, params, problem, solver = _mms_problem(n, J, theta, dt, T)
+    o = _oracle_twin(n, params, theta, dt, T)
+    time = problem.time
+    problem.f = Expression(("sin(2*x[0])*x[1]*(1+t)", "exp(x[2]) + pow(x[0], 3)", "cos(x[0] + 2*x[1]*x[2])"), t=time,
+                           degree=df)
+    problem.g = [Expression("(1+%d)*sin(3*x[0])*cos(x[1])*(1+t) + pow(x[2], 4)" % i, t=time, degree=dg) for i in range(J)]
+    o.f = Coef(fn=lambda x, t: np.stack([np.sin(2 * x[:, 0]) * x[:, 1] * (1 + t), np.exp(x[:, 2]) + x[:, 0] ** 3,
+                                         np.cos(x[:, 0] + 2 * x[:, 1] * x[:, 2])], 1), degree=df)
+    o.g = [Coef(fn=lambda x, t, i=i: (1 + i) * np.sin(3 * x[:, 0]) * np.cos(x[:, 1]) * (1 + t) + x[:, 2] ** 4, degree=dg)
+           for i in range(J)]
+    _init(solver, o)
+    solver._assemble_system()
+    bo, dofs, vals = o.rhs(0.0)
+    bcs = solver.bcs[0] + solver.bcs[1]
+    solver._sync_dirichlet(bcs)
+    b = solver._rhs(problem.time, 0.0, dt, theta, bcs).get_local()
+    assert _rel(b, bo) < 1e-12, _rel(b, bo)
+    solver.engine.close()

@@ -79,3 +79,67 @@ def test_elastic_stress_of_a_quadratic_field():
     eps = 0.5 * (grad + np.swapaxes(grad, 1, 2))
     ref = 2 * mu * eps + lm * np.trace(grad, axis1=1, axis2=2)[:, None, None] * np.eye(3)
     assert np.allclose(sig, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_user_subdomain_inside_reference_style():
+    """A Python ``SubDomain`` written the DOLFIN way (``x[0]`` = first coordinate of ONE point, ``and`` / ``or`` on
+    coordinates, src/mpet/demo/*: ``near(x[0], 0.0) and on_boundary``) marks the same facets as the equivalent
+    CompiledSubDomain string (it used to index the first POINT)."""
+    from waterscapes_b200.mpet.dolfin_shim import SubDomain, near
+
+    class Left(SubDomain):                       # vectorises: evaluated on all points at once
+        def inside(self, x, on_boundary):
+            return on_boundary and near(x[0], 0.0)
+
+    class LeftLower(SubDomain):                  # `and` on two coordinate tests: only works point by point
+        def inside(self, x, on_boundary):
+            return near(x[0], 0.0) and x[2] < 0.5 + 1e-12
+
+    mesh = UnitCubeMesh(4)
+    a, b = MeshFunction("size_t", mesh, 2, 0), MeshFunction("size_t", mesh, 2, 0)
+    Left().mark(a, 1)
+    CompiledSubDomain("on_boundary && near(x[0], 0.0)").mark(b, 1)
+    assert a.array_.sum() == 2 * 16 and np.array_equal(a.array_, b.array_)
+    a, b = MeshFunction("size_t", mesh, 2, 0), MeshFunction("size_t", mesh, 2, 0)
+    LeftLower().mark(a, 1)
+    CompiledSubDomain("near(x[0], 0.0) && x[2] < 0.5 + 1e-12").mark(b, 1)
+    assert a.array_.sum() == 2 * 8 and np.array_equal(a.array_, b.array_)
+
+
+@pytest.mark.parametrize("degree", [0, 1, 3, 4])
+def test_cell_load_operator_matches_oracle_quadrature(degree):
+    """Expression(degree=d) source data (the reference's MMS tests use d = 3, test_convergence_mpetsolver.py:129-131):
+    the host-built cell-lattice operator times the lattice values == the oracle's int f.v dx / int g q dx with the
+    coefficient interpolated cell-wise into P_d and integrated by a rule exact for degree (test + d)."""
+    import scipy.sparse as sps
+    from waterscapes_b200.mpet.dolfin_shim import FunctionSpace, Mesh
+    from waterscapes_b200.mpet.la import CellLoadOperator
+    om = unit_cube_mesh(3, jitter=0.2)
+    o = MPETOracle(om, dict(J=1, E=1.0, nu=0.3, alpha=(1.0,), c=(1.0,), K=(1.0,), S=((0.0,),)), dt=0.1, theta=1.0)
+    space = FunctionSpace.from_host(Mesh(om.coords, om.cells), 1)
+    f = lambda x, t=0.0: np.stack([np.sin(2 * x[:, 0]) * x[:, 1], np.exp(x[:, 2]) + x[:, 0] ** 3,
+                                   np.cos(x[:, 0] + 2 * x[:, 1] * x[:, 2])], axis=1)
+    g = lambda x, t=0.0: np.sin(3 * x[:, 0]) * np.cos(x[:, 1]) + x[:, 2] ** 4
+
+    class E:                                     # stands in for dolfin_shim.Expression (only eval_points is used)
+        def __init__(self, fn):
+            self.fn = fn
+
+        def eval_points(self, x):
+            return self.fn(x)
+
+    def apply(op, data, nrows):
+        rp, ci, v = (t.numpy() for t in op.csr)
+        return sps.csr_matrix((v, ci, rp), shape=(nrows, data.shape[-1])) @ data
+
+    op2 = CellLoadOperator(space, True, degree, device="cpu")
+    d2 = op2.data(E(f))
+    ref = o._cell_load(Coef(fn=lambda x, t: f(x), degree=degree), 0.0, "u")
+    for k in range(3):
+        got = apply(op2, d2[k], space.N2)
+        want = ref[o.space.u_dofs(k)]
+        assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want), (degree, k)
+    op1 = CellLoadOperator(space, False, degree, device="cpu")
+    got = apply(op1, op1.data(E(g)), space.Nv)
+    want = o._cell_load(Coef(fn=lambda x, t: g(x), degree=degree), 0.0, ("p", 0))[o.space.p_dofs(0)]
+    assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want), degree

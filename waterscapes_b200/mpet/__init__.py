@@ -6,7 +6,7 @@ _lib.load()
 
 from .dolfin_shim import (Mesh, BoxMesh, UnitCubeMesh, Constant, Expression, FacetNormal, MeshFunction,  # noqa
                           SubDomain, CompiledSubDomain, Function, FunctionSpace, DirichletBC, Parameters,
-                          parameters, interpolate, assign, info, warning, INVALID, CellFunction)
+                          parameters, interpolate, assign, info, warning, INVALID, CellFunction, near, DOLFIN_EPS)
 from .la import assemble, LUSolver, PETScKrylovSolver, Matrix, Form  # noqa
 from .mpetproblem import MPETProblem, convert_to_E_nu, convert_to_mu_lmbda, elastic_stress  # noqa
 from .mpetsolver import MPETSolver, DIRICHLET_MARKER, NEUMANN_MARKER, ROBIN_MARKER  # noqa

@@ -239,10 +239,11 @@ class MeshFunction:
     """Facet markers (``MeshFunction("size_t", mesh, 2)``), stored over EXTERIOR facets only --
     the only facets the MPET forms integrate over (ds) or constrain."""
 
-    def __init__(self, value_type, mesh, dim):
+    def __init__(self, value_type, mesh, dim, value=None):
         assert dim == 2, "only facet markers are used by the mpet API"
         self.mesh = mesh
-        self.array_ = np.full(mesh.exterior_facets()["cell"].shape[0], INVALID, dtype=np.int64)
+        self.array_ = np.full(mesh.exterior_facets()["cell"].shape[0], INVALID if value is None else value,
+                              dtype=np.int64)
 
     def set_all(self, v):
         self.array_[:] = v
@@ -251,11 +252,42 @@ class MeshFunction:
         return self.array_
 
 
+DOLFIN_EPS = 3.0e-16
+
+
+def near(a, b, eps=DOLFIN_EPS):
+    """DOLFIN's ``near(a, b, eps)``; works on numbers and on arrays of coordinates."""
+    return np.abs(np.asarray(a) - b) < eps
+
+
+class _Points(np.ndarray):
+    """Coordinates of npts points [npts, 3] handed to a user-written ``SubDomain.inside(x, on_boundary)``.
+    DOLFIN calls ``inside`` with ONE point, so reference-style code writes ``x[0]`` for the first COORDINATE;
+    an integer index therefore selects a column here (the coordinate of all points), not a row."""
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            return np.asarray(self)[:, i]
+        return np.asarray(self)[i]
+
+
 class SubDomain:
-    """Boundary predicate; ``inside(x, on_boundary)`` vectorised over points x[npts, 3]."""
+    """Boundary predicate.  ``inside(x, on_boundary)`` as in DOLFIN: ``x[k]`` is the k-th coordinate.  It is
+    evaluated on all points of the boundary facets at once (``x[k]`` is then an array); an ``inside`` that only
+    works on one point (``and`` / ``or`` / ``if`` on coordinates) is detected and called point by point."""
 
     def inside(self, x, on_boundary):
         raise NotImplementedError
+
+    def _inside_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=float)
+        try:
+            r = np.asarray(self.inside(pts.view(_Points), True))
+            if r.dtype != object and r.shape in ((), (pts.shape[0],)):
+                return np.broadcast_to(r.astype(bool), (pts.shape[0],))
+        except (ValueError, TypeError):      # "truth value of an array is ambiguous": scalar-style predicate
+            pass
+        return np.fromiter((bool(self.inside(p, True)) for p in pts), dtype=bool, count=pts.shape[0])
 
     def mark(self, markers, value):
         mesh = markers.mesh
@@ -263,8 +295,8 @@ class SubDomain:
         xs = mesh.coordinates[fv]                                 # [Nf, 3, 3]
         ok = np.ones(fv.shape[0], dtype=bool)
         for k in range(3):                                        # all vertices and the midpoint inside
-            ok &= np.asarray(self.inside(xs[:, k], True), dtype=bool)
-        ok &= np.asarray(self.inside(xs.mean(axis=1), True), dtype=bool)
+            ok &= self._inside_points(xs[:, k])
+        ok &= self._inside_points(xs.mean(axis=1))
         markers.array_[ok] = value
 
 

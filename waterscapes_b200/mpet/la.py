@@ -47,6 +47,82 @@ def _host_csr(rows, cols, vals, nrows, device):
             torch.as_tensor(vals, device=device))
 
 
+def _lattice(degree):
+    """Nodes of P_degree on the reference tet (degree 0: barycentre), as reference coordinates [nd, 3]."""
+    if degree == 0:
+        return np.full((1, 3), 0.25)
+    pts = [(i, j, k) for i in range(degree + 1) for j in range(degree + 1 - i) for k in range(degree + 1 - i - j)]
+    return np.asarray(pts, dtype=float) / degree
+
+
+def _monomial_coefficients(nodes, degree):
+    """Lagrange basis on ``nodes`` in the monomial basis of total degree <= degree: column n = basis function n."""
+    expo = [(i, j, k) for i in range(degree + 1) for j in range(degree + 1 - i) for k in range(degree + 1 - i - j)]
+    V = np.stack([nodes[:, 0] ** a * nodes[:, 1] ** b * nodes[:, 2] ** c for a, b, c in expo], axis=1)
+    return np.linalg.inv(V), expo
+
+
+def reference_mass(test_degree, data_degree):
+    """int over the reference tet of (P_test basis a) * (P_data basis n), exactly (monomial integrals
+    a! b! c! / (a + b + c + 3)!).  Test basis in UFC order: vertices, then the edges (2,3), (1,3), (1,2), (0,3),
+    (0,2), (0,1); data basis on the lattice of _lattice(data_degree)."""
+    from math import factorial
+    vert = np.array([[0., 0., 0.], [1., 0., 0.], [0., 1., 0.], [0., 0., 1.]])
+    if test_degree == 1:
+        tn = vert
+    else:
+        mids = [0.5 * (vert[a] + vert[b]) for a, b in ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))]
+        tn = np.vstack([vert, mids])
+    Ct, et = _monomial_coefficients(tn, test_degree)
+    Cd, ed = _monomial_coefficients(_lattice(data_degree), data_degree)
+    G = np.array([[factorial(a + p) * factorial(b + q) * factorial(c + r) / factorial(a + p + b + q + c + r + 3)
+                   for (p, q, r) in ed] for (a, b, c) in et])
+    return Ct.T @ G @ Cd
+
+
+class CellLoadOperator:
+    """int coef * test dx for a coefficient whose DOLFIN interpolation degree d differs from the test space's:
+    ``Expression(..., degree=d)`` is interpolated CELL BY CELL into P_d (discontinuous across cells) and the product
+    with the test function integrated exactly -- what FFC's quadrature of degree (test + d) does for the
+    reference's ``f``, ``g`` (test_convergence_mpetsolver.py:129-131 uses degree 3).  Stored as a device CSR
+    operator [test nodes] x [Nc * nd cell-lattice points] with entries |det J_c| * Mhat[a, n], built once per
+    (space, degree) on the host and applied with mpet_csr_spmv, like the facet operators."""
+
+    def __init__(self, space, p2, degree, device=None):
+        mesh = space.mesh
+        cells = mesh.cells.astype(np.int64)
+        x = mesh.coordinates
+        nc = cells.shape[0]
+        xc = x[cells]                                               # [nc, 4, 3]
+        detj = np.abs(np.linalg.det(xc[:, 1:, :] - xc[:, :1, :]))
+        if p2:
+            nodes = np.concatenate([cells] + [space.Nv + space.edge_index(cells[:, a], cells[:, b])[:, None]
+                                              for a, b in ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))], axis=1)
+            nrows = space.N2
+        else:
+            nodes, nrows = cells, space.Nv
+        M = reference_mass(2 if p2 else 1, degree)                  # [nt, nd]
+        nt, nd = M.shape
+        ref = _lattice(degree)
+        lam = np.concatenate([1.0 - ref.sum(axis=1, keepdims=True), ref], axis=1)      # barycentric [nd, 4]
+        self.points = np.einsum("nv,cvd->cnd", lam, xc).reshape(-1, 3)                 # [nc * nd, 3]
+        rows = np.repeat(nodes[:, :, None], nd, axis=2).ravel()
+        cols = np.repeat((np.arange(nc)[:, None] * nd + np.arange(nd)[None, :])[:, None, :], nt, axis=1).ravel()
+        vals = (detj[:, None, None] * M[None]).ravel()
+        self.csr = _host_csr(rows, cols, vals, nrows, device if device is not None else space.engine.device)
+        self.nd = nd
+
+    def data(self, coef):
+        """Values of ``coef`` at the cell-lattice points (scalar: [nc*nd]; vector: [3, nc*nd])."""
+        v = np.asarray(coef.eval_points(self.points), dtype=float)
+        return v.T if v.ndim == 2 else v
+
+    def apply(self, engine, data, y, scale=1.0):
+        """y += scale * Q data   (y: device slice over the test space's nodes)."""
+        d = torch.as_tensor(np.ascontiguousarray(data * scale), device=engine.device)
+        engine.csr_spmv(self.csr[0], self.csr[1], self.csr[2], d, y, beta=1.0)
+
+
 class FacetOperator:
     """int_{facets with marker} data * test ds as a device CSR operator acting on per-facet nodal data.
     Built once per marker set on the host (O(N^(2/3)) facets), applied on the device every step."""

@@ -15,7 +15,7 @@ import torch
 from ..engine import Engine
 from .dolfin_shim import (Constant, Expression, NormalProduct, Function, FunctionSpace, DirichletBC,
                           Parameters, CellFunction, info, warning)
-from .la import (Form, Matrix, AssembledVector, RobinEntries, FacetOperator, assemble, LUSolver,
+from .la import (Form, Matrix, AssembledVector, RobinEntries, FacetOperator, CellLoadOperator, assemble, LUSolver,
                  PETScKrylovSolver, apply_symmetric, _is_zero, _M3, NEUMANN_MARKER as _N, ROBIN_MARKER as _R)
 from .mpetproblem import convert_to_mu_lmbda
 
@@ -25,8 +25,15 @@ NEUMANN_MARKER = 1
 ROBIN_MARKER = 2
 
 
-def _f(v):
-    return float(v)
+def _f(v, what="material parameter"):
+    """Constant coefficient as a number.  The reference lets E, nu, alpha, c, K, S and beta be UFL coefficients
+    (Expression / Function); the kernels here integrate constant coefficients exactly (K additionally as a DG0
+    CellFunction), so anything else is refused loudly instead of being mis-read."""
+    try:
+        return float(v)
+    except (TypeError, ValueError):
+        raise NotImplementedError("%s must be a number or Constant on the B200 path (got %s); spatially varying "
+                                  "K is supported as a DG0 CellFunction" % (what, type(v).__name__)) from None
 
 
 class MPETSolver(object):
@@ -45,6 +52,7 @@ class MPETSolver(object):
         self.engine = Engine(device)
         self.partition = partition          # waterscapes_b200.parallel.Partition (multi-GPU) or None
         self._engine_bc_dofs = None
+        self._cell_ops = {}                 # (scalar space, degree) -> CellLoadOperator
         self._pc_dirty = True
         self._krylov_cfg = None
         self._prec_assembled_for = None
@@ -138,7 +146,7 @@ class MPETSolver(object):
         dg0 = {i: v for i, v in enumerate(p["K"]) if isinstance(v, CellFunction)}
         Ks = [1.0 if i in dg0 else _f(v) for i, v in enumerate(p["K"])]
         cells_key = tuple((i, hash(v.values.tobytes())) for i, v in sorted(dg0.items()))
-        vals = (float(p["E"]), float(p["nu"]), [_f(v) for v in p["alpha"]], Ks,
+        vals = (_f(p["E"], "E"), _f(p["nu"], "nu"), [_f(v, "alpha") for v in p["alpha"]], Ks,
                 [[_f(v) for v in row] for row in p["S"]], [_f(v) for v in p["c"]], float(self.dt),
                 float(self.params["theta"]))
         if getattr(self, "_pushed", None) != vals + (cells_key,):
@@ -250,9 +258,28 @@ class MPETSolver(object):
             v = float(coef)
             if v != 0.0:
                 y.add_(self._lumped_vec(space), alpha=scale * v)
+        elif self._cell_op_degree(coef, space) is not None:
+            op = self._cell_op(space, self._cell_op_degree(coef, space))
+            op.apply(self.engine, op.data(coef), y, scale=scale)
         else:
             vals = torch.as_tensor(np.asarray(coef.eval_points(pts), dtype=float), device=y.device)
             self.engine.mass_apply(space, scale, vals, y)
+
+    @staticmethod
+    def _cell_op_degree(coef, space):
+        """Interpolation degree of a coefficient that needs the cell-lattice operator: DOLFIN interpolates
+        ``Expression(degree=d)`` into P_d cell by cell; for d == the test space's degree (or no degree given) that is
+        the nodal data the mass operator already takes."""
+        d = getattr(coef, "degree", None)
+        if d is None or int(d) == (2 if space == 2 else 1):
+            return None
+        return int(d)
+
+    def _cell_op(self, space, degree):
+        key = (space, degree)
+        if key not in self._cell_ops:
+            self._cell_ops[key] = CellLoadOperator(self.VQ, space == 2, degree)
+        return self._cell_ops[key]
 
     # ------------------------------------------------------------------ pieces of the forms
     def _robin_entries(self, i):
@@ -261,7 +288,7 @@ class MPETSolver(object):
         sp = self.VQ
         dt, theta = float(self.dt), float(self.params["theta"])
         op = self._facet_op("c", i, ROBIN_MARKER, False)
-        beta = float(self.problem.beta[i])
+        beta = _f(self.problem.beta[i], "the Robin coefficient beta")
         if op.nf == 0 or beta == 0.0:
             return RobinEntries(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
         lo, _ = sp.sub_range(self._net_sub(i))
@@ -291,7 +318,7 @@ class MPETSolver(object):
         rhs(L2[i]) in mpettotalpressuresolver.py:323)."""
         sp, eng = self.VQ, self.engine
         dt, theta = float(self.dt), float(self.params["theta"])
-        beta = float(self.problem.beta[i])
+        beta = _f(self.problem.beta[i], "the Robin coefficient beta")
         if beta == 0.0:
             return
         op = self._facet_op("c", i, ROBIN_MARKER, False)
@@ -333,6 +360,11 @@ class MPETSolver(object):
                 for k in range(3):
                     if fv[k] != 0.0:
                         b[k * sp.N2:(k + 1) * sp.N2].add_(self._lumped_vec(2), alpha=float(fv[k]))
+            elif self._cell_op_degree(f, 2) is not None:
+                op = self._cell_op(2, self._cell_op_degree(f, 2))
+                d = op.data(f)
+                for k in range(3):
+                    op.apply(eng, d[k], b[k * sp.N2:(k + 1) * sp.N2])
             else:
                 vals = np.asarray(f.eval_points(sp.node2_coordinates()), dtype=float)
                 for k in range(3):
