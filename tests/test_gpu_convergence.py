@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 from tests import mms3d
 
 
-def _single_run(n, M, theta, total_pressure):
+def _single_run(n, M, theta, total_pressure, df=3, dg=3):
     import waterscapes_b200.mpet as mpet
     from waterscapes_b200.mpet import (MPETProblem, UnitCubeMesh, Constant, Expression, CompiledSubDomain, FacetNormal,
                                        interpolate, assign)
@@ -28,9 +28,9 @@ def _single_run(n, M, theta, total_pressure):
     mesh = UnitCubeMesh(n)
     time = Constant(0.0)
     problem = MPETProblem(mesh, time, params=params)
-    problem.f = Expression(lambda x, t: ex["f"](x, t), t=time, degree=3)
+    problem.f = Expression(lambda x, t: ex["f"](x, t), t=time, degree=df)
     problem.f.value_shape = lambda: (3,)
-    problem.g = [Expression(lambda x, t, i=i: ex["g"][i](x, t), t=time, degree=3) for i in range(2)]
+    problem.g = [Expression(lambda x, t, i=i: ex["g"][i](x, t), t=time, degree=dg) for i in range(2)]
     problem.u_bar = Expression(lambda x, t: ex["u"](x, t), t=time, degree=3)
     problem.u_bar.value_shape = lambda: (3,)
     problem.p_bar = [Expression(lambda x, t, i=i: ex["p"][i](x, t), t=time, degree=3) for i in range(2)]
@@ -66,10 +66,14 @@ def _single_run(n, M, theta, total_pressure):
 
 
 @pytest.mark.parametrize("solver_kind", ["standard", "total_pressure"])
-@pytest.mark.parametrize("theta,ns,ms", [(0.5, [8, 16, 32], [4, 8, 16]), (1.0, [8, 16, 32], [8, 32, 128])])
-def test_mms_convergence_rates_3d(solver_kind, theta, ns, ms):
+@pytest.mark.parametrize("theta,ns,ms,df,dg", [(0.5, [8, 16, 32], [4, 8, 16], 3, 3), (1.0, [8, 16, 32], [8, 32, 128], 2, 1)])
+def test_mms_convergence_rates_3d(solver_kind, theta, ns, ms, df, dg):
+    """Source data f, g: ``Expression(degree=3)`` as in the reference's tests (:129-131) on the Crank-Nicolson grid
+    -- cell-wise P3 interpolation integrated exactly, 912 673 distinct lattice points per evaluation at n = 32 --;
+    the 128-step implicit-Euler grid takes nodal (P2 / P1) data, which keeps its host-side evaluation of the
+    sympy-derived sources 5x shorter (the thresholds are the reference's either way)."""
     tp = solver_kind == "total_pressure"
-    res = [_single_run(n, m, theta, tp) for n, m in zip(ns, ms)]
+    res = [_single_run(n, m, theta, tp, df, dg) for n, m in zip(ns, ms)]
     hs = [r[1] for r in res]
     u_L2 = mms3d.rates([r[0]["u_L2"] for r in res], hs)
     u_H1 = mms3d.rates([r[0]["u_H1"] for r in res], hs)

@@ -105,7 +105,16 @@ class CellLoadOperator:
         nt, nd = M.shape
         ref = _lattice(degree)
         lam = np.concatenate([1.0 - ref.sum(axis=1, keepdims=True), ref], axis=1)      # barycentric [nd, 4]
-        self.points = np.einsum("nv,cvd->cnd", lam, xc).reshape(-1, 3)                 # [nc * nd, 3]
+        pts = np.einsum("nv,cvd->cnd", lam, xc).reshape(-1, 3)                         # [nc * nd, 3]
+        # lattice points on shared vertices / edges / faces coincide between cells (P3: 120 Nv cell-wise points, ~27 Nv
+        # distinct ones): the coefficient is evaluated once per distinct point.  Points are identified on a grid of
+        # 1e-10 of the mesh extent -- far below the lattice spacing; two copies of one point that straddle a grid
+        # line are simply both evaluated.
+        ext = float(np.max(x.max(axis=0) - x.min(axis=0))) or 1.0
+        q = np.ascontiguousarray(np.round((pts - x.min(axis=0)) / (1e-10 * ext)).astype(np.int64))
+        _, first, inverse = np.unique(q.view([("", np.int64)] * 3).ravel(), return_index=True, return_inverse=True)
+        self.points = pts[first]                                                       # distinct points
+        self.expand = inverse.ravel()                                                  # cell-lattice point -> distinct
         rows = np.repeat(nodes[:, :, None], nd, axis=2).ravel()
         cols = np.repeat((np.arange(nc)[:, None] * nd + np.arange(nd)[None, :])[:, None, :], nt, axis=1).ravel()
         vals = (detj[:, None, None] * M[None]).ravel()
@@ -114,7 +123,7 @@ class CellLoadOperator:
 
     def data(self, coef):
         """Values of ``coef`` at the cell-lattice points (scalar: [nc*nd]; vector: [3, nc*nd])."""
-        v = np.asarray(coef.eval_points(self.points), dtype=float)
+        v = np.asarray(coef.eval_points(self.points), dtype=float)[self.expand]
         return v.T if v.ndim == 2 else v
 
     def apply(self, engine, data, y, scale=1.0):
