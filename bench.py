@@ -25,6 +25,7 @@ UNIT = "DOF/s"
 DEFAULT_CONFIG = "cfg5"          # A=3, n=72 per GPU: ~10.3 M dofs per GPU (BASELINE.json configs[4])
 CPU_SAMPLE_N = 32                # bounded CPU sample of the same workload family (966 k dofs; ~5 s per step on 32 cores)
 CPU_TREND_NS = (12, 20)          # two more CPU sizes: the DOF/s trend towards the bench size is evidence, not hope
+CONFIG_N = {"cfg1": 8, "cfg2": 34, "cfg3": 28, "cfg4": 71, "cfg5": 72}      # waterscapes_b200/workloads.py CONFIGS
 
 
 def parse_args():
@@ -101,6 +102,16 @@ class ClockSampler:
             out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                    "samples": len(sm)}
         return out
+
+
+def workload_string(config, n, rtol):
+    """The workload both arms name (the reference arm times a bounded sample of it, `cpu_baseline.sample`).  Sizes from
+    the closed forms of SURVEY.md section 8 so that the CPU arm needs no engine."""
+    J = {"cfg1": 2, "cfg2": 1, "cfg3": 4, "cfg4": 4, "cfg5": 3}[config]
+    dofs = 3 * (2 * n + 1) ** 3 + J * (n + 1) ** 3
+    return ("%s: [P2]^3x[P1]^%d MPET on BoxMesh(%d^3) per GPU, %d cells, %d dofs per GPU; step = assemble A + b, "
+            "Dirichlet, MINRES+block-AMG to rtol %g (PETSc default test: relative to the preconditioned norm of b)"
+            % (config, J, n, 6 * n ** 3, dofs, rtol))
 
 
 def measured_peak():
@@ -455,7 +466,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": c["sec"] * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: %s" % (args.config, sample), "rtol": args.rtol,
+                "config": {"workload": workload_string(args.config, args.n or CONFIG_N[args.config], args.rtol),
+                           "sample": sample, "rtol": args.rtol,
                            "amg_setup_s_excluded": round(c["setup_s"], 2),
                            "note": "CPU restatement (OpenMP cell loop + OpenMP CSR products, oracle/) of the reference "
                                    "path; DOLFIN/PETSc are not installable offline.  Same workload family, tolerance "
@@ -632,11 +644,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"formulation": args.formulation,
-                       "workload": "%s: [P2]^3x[P1]^%d MPET on BoxMesh(%d^3) per GPU, %d cells, %d dofs, %d nnz; "
-                                   "step = assemble A + b, Dirichlet, MINRES+block-AMG to rtol %g (PETSc default test: "
-                                   "relative to the preconditioned norm of b)"
-                                   % (args.config, S["A"], n, S["Nc"], N, S["nnz"], args.rtol),
-                       "dofs_per_gpu": N, "nnz_per_gpu": S["nnz"], "rtol": args.rtol, "krylov_iterations": iters,
+                       "workload": workload_string(args.config, n, args.rtol),
+                       "dofs_per_gpu": N, "cells_per_gpu": S["Nc"], "nnz_per_gpu": S["nnz"], "rtol": args.rtol,
+                       "krylov_iterations": iters,
                        "krylov_iterations_e2e": iters_e2e,
                        "parallelism": "1 GPU" if world == 1 else "cube refined to %d^3 cubes, %dx%dx%d bricks (own cells + 1 ghost layer), %s halo exchange + all-reduced dots, distributed V-cycles" % ((int(round(n * world ** (1.0 / 3.0))),) + tuple(grid) + (eng.comm_kind(),)),
                        "total_dofs": total_dofs,
