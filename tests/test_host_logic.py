@@ -143,3 +143,30 @@ def test_cell_load_operator_matches_oracle_quadrature(degree):
     got = apply(op1, op1.data(E(g)), space.Nv)
     want = o._cell_load(Coef(fn=lambda x, t: g(x), degree=degree), 0.0, ("p", 0))[o.space.p_dofs(0)]
     assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want), degree
+
+
+def test_rigid_motions_match_oracle_and_are_l2_orthonormal():
+    """waterscapes_b200/mpet/rm_basis_L2.py (host-side twin of rm_basis_L2.py:10-74) against the oracle's
+    independent implementation, and the defining property: the six motions are orthonormal in L2(Omega)."""
+    from waterscapes_b200.mpet.dolfin_shim import Mesh
+    from waterscapes_b200.mpet.rm_basis_L2 import rigid_motions
+    om = unit_cube_mesh(3, jitter=0.2)
+    om.coords[:] = om.coords * np.array([3.0, 2.0, 1.0]) + np.array([0.5, -1.0, 2.0])
+    o = MPETOracle(om, dict(J=1, E=1.0, nu=0.3, alpha=(1.0,), c=(1.0,), K=(1.0,), S=((0.0,),)), dt=0.1, theta=1.0)
+    Z = rigid_motions(Mesh(om.coords, om.cells))
+    Zo = o.rigid_motions()
+    x = np.random.default_rng(2).uniform(0, 3, size=(50, 3))
+    assert len(Z) == len(Zo) == 6
+    for a, b in zip(Z, Zo):      # eigenvectors are defined up to sign
+        va, vb = a(x), b(x)
+        assert min(np.abs(va - vb).max(), np.abs(va + vb).max()) < 1e-10
+    # Gram matrix with the degree-2 rule (the motions are affine: exact)
+    xc = om.coords[om.cells]
+    vol = om.cell_volumes()
+    a_, b_ = 0.1381966011250105, 0.5854101966249685
+    lam = np.array([[b_, a_, a_, a_], [a_, b_, a_, a_], [a_, a_, b_, a_], [a_, a_, a_, b_]])
+    xq = np.einsum("qv,cvd->cqd", lam, xc).reshape(-1, 3)
+    w = np.repeat(vol / 4.0, 4)
+    vals = [z(xq) for z in Z]
+    G = np.array([[np.sum(w * np.einsum("pd,pd->p", vi, vj)) for vj in vals] for vi in vals])
+    assert np.abs(G - np.eye(6)).max() < 1e-12
