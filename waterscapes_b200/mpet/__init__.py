@@ -12,4 +12,5 @@ from .mpetproblem import MPETProblem, convert_to_E_nu, convert_to_mu_lmbda, elas
 from .mpetsolver import MPETSolver, DIRICHLET_MARKER, NEUMANN_MARKER, ROBIN_MARKER  # noqa
 from .mpettotalpressuresolver import MPETTotalPressureSolver  # noqa
 from .bc_symmetric import get_bc_dofs, zero_rows_cols, apply_symmetric  # noqa
+from .rm_basis_L2 import rigid_motions  # noqa  (src/mpet/mpet/__init__.py:15)
 from .hdf5 import HDF5File  # noqa
