@@ -265,24 +265,8 @@ def assemble(form):
     return form.solver._assemble(form)
 
 
-# --------------------------------------------------------------------------- bc_symmetric.py mirror
-def get_bc_dofs(bc):
-    """bc_symmetric.py:6-8."""
-    return np.array(list(bc.get_boundary_values().keys()), dtype=np.intc)
-
-
-def zero_rows_cols(dofs, A, b=None):
-    """bc_symmetric.py:11-18 (MatZeroRowsColumns): recorded on the handle; the right-hand side is
-    corrected inside the solve through the initial residual (x carries the boundary values)."""
-    A.symmetric = True
-    A._sym_dofs = np.asarray(dofs)
-
-
-def apply_symmetric(bc, A, b=None):
-    """bc_symmetric.py:20-22."""
-    if bc not in A.bcs:
-        A.bcs.append(bc)
-    zero_rows_cols(bc.dofs(), A, b)
+# bc_symmetric.py mirror: lives in its own module like the reference's, re-exported here for the solvers
+from .bc_symmetric import get_bc_dofs, zero_rows_cols, apply_symmetric  # noqa: E402,F401
 
 
 # --------------------------------------------------------------------------- solver objects
